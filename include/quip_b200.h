@@ -1,0 +1,127 @@
+/*
+ * quip_b200 -- C ABI of the B200-native packed QuantLinear path.
+ *
+ * This is the boundary the reference's FFI for this path would bind.  The
+ * reference (Cornell-RelaxML/QuIP) has exactly one native call site on the
+ * path, the absent `quant_cuda` extension:
+ *
+ *     quant_cuda.vecquant3matmul(x, qweight, y, scales, zeros)   quant.py:229-230
+ *     quant_cuda.vecquant4matmul(x, qweight, y, scales, zeros)   zeroShot/models/quant.py:207-208
+ *
+ * i.e. "y += (scales*code - zeros) . x" on a packed-integer matrix, called from
+ * Quant3Linear.forward (quant.py:222-233).  quip_qlinear_forward() replaces that
+ * call and, in the same launch sequence, the work the reference folds into its
+ * dense fp16 weight at quantization time (method.py:195-214): the scaleWH
+ * rescale and the U / V incoherence un-projection.  quip_pack_codes() replaces
+ * the CPU/numpy packer Quant3Linear.pack (quant.py:185-220, TODO at opt.py:302);
+ * quip_convert_ref() reads the reference's own 3-/4-bit layouts.
+ *
+ * Conventions: plain pointers and sizes, no torch types.  All data pointers are
+ * DEVICE pointers unless a parameter says "host"; the caller owns every buffer;
+ * calls are asynchronous on the `stream` handle (a cudaStream_t cast to void*);
+ * no internal allocation -- scratch comes from the caller-provided workspace.
+ * Every function returns 0 on success and a non-zero code on error, with a
+ * human-readable message available from quip_last_error() (thread-local).
+ * There is no CPU fallback: on a machine without an sm_100 device the launch
+ * entry points return QUIP_ERR_CUDA.
+ */
+#ifndef QUIP_B200_H_
+#define QUIP_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QUIP_ABI_VERSION 1
+
+enum {
+  QUIP_OK = 0,
+  QUIP_ERR_ARG = 1,        /* bad shape / null pointer / unsupported bits */
+  QUIP_ERR_WORKSPACE = 2,  /* workspace too small */
+  QUIP_ERR_CUDA = 3,       /* CUDA runtime / driver error (message has the detail) */
+  QUIP_ERR_UNSUPPORTED = 4
+};
+
+/* One block-diagonal pass of a butterfly (reference method.py:58-63).
+ * A side of size n is viewed as nblk blocks of p elements; block b is
+ * multiplied by its own (or the shared) p x p factor:
+ *     out[pos(b,i)] = sum_j factors[b or 0][i][j] * in[pos(b,j)]
+ * pos(b,j) = b*p + j (strided == 0) or j*nblk + b (strided == 1). */
+typedef struct {
+  int32_t p;
+  int32_t nblk;
+  int32_t strided;
+  int32_t shared;          /* 1: a single factor for every block (method.py:38-39, "noblock") */
+  const void* factors;     /* fp16 [shared ? 1 : nblk][p][p], row-major */
+} QuipPass;
+
+/* One incoherence side: V acts on the K input features, U on the N outputs.
+ * n == 0 means the side is absent (no --pre_proj). */
+typedef struct {
+  int32_t n;
+  int32_t npass;           /* 0..2 */
+  QuipPass pass[2];        /* execution order */
+  const int32_t* idx;      /* gather index, length n, or NULL for identity:
+                              V: layout[l] = x[idx[l]] ; U: y[j] = layout[idx[j]] */
+} QuipSide;
+
+/* A packed linear layer  y = ((x * inv_scale) V^T) Q^T U + bias,
+ * Q[n][k] = scales[n]*code[n][k] - zeros[n]  (Quant3Linear convention, quant.py:186-191).
+ * qweight is in the native fragment-major layout (oracle/packing.py), rows
+ * and columns already in the U / V layout order, scales/zeros in the same row order. */
+typedef struct {
+  int32_t K, N, bits;      /* bits in {2,3,4}; K % 128 == 0; N % 16 == 0 */
+  int32_t flags;           /* QUIP_FLAG_* */
+  const int32_t* qweight;
+  const float* scales;     /* (N) */
+  const float* zeros;      /* (N) */
+  const void* bias;        /* fp16 (N) in output-feature order, or NULL */
+  const float* inv_scale;  /* fp32 (K) = 1/scaleWH in input-feature order, or NULL */
+  QuipSide V, U;
+} QuipLinearDesc;
+
+#define QUIP_FLAG_SYMMETRIC 1   /* scales*cbar == zeros for every row: the row-sum term vanishes (qfn 'b') */
+
+/* y (M,N) fp16 = forward of x (M,K) fp16.  Replaces Quant3Linear.forward's
+ * vecquant3matmul call (quant.py:222-233) for any M >= 1. */
+int quip_qlinear_forward(const QuipLinearDesc* d, const void* x, void* y, int64_t M,
+                         void* workspace, size_t workspace_bytes, void* stream);
+int quip_qlinear_workspace_bytes(const QuipLinearDesc* d, int64_t M, size_t* out_bytes);
+
+/* Building blocks (also exported for tests and micro-benchmarks). */
+/* z (M,N) fp16 = x2 (M,K) fp16 contracted with the packed matrix + affine epilogue (+bias if given).
+ * xsum (M) fp32 row sums of x2, required unless QUIP_FLAG_SYMMETRIC.  path: 0 auto, 1 mma.sync skinny
+ * kernel, 2 tcgen05 kernel. */
+int quip_qgemm(const QuipLinearDesc* d, const void* x2, const float* xsum, const void* bias,
+               void* z, int64_t M, int path, void* workspace, size_t workspace_bytes, void* stream);
+int quip_rowsum(const void* x, float* xsum, int64_t M, int32_t K, void* stream);
+/* out[m][l] = in[m][idx[l]] * scale[idx[l]] (+ bias[l]);  idx / scale / bias may be NULL. */
+int quip_gather(const void* in, void* out, int64_t M, int32_t n, const int32_t* idx,
+                const float* scale, const void* bias, void* stream);
+/* impl: 0 auto, 1 generic CUDA-core kernel, 2 tensor-core kernels only */
+int quip_rot_pass(const QuipPass* pass, const void* in, void* out, int64_t M, int32_t n, int impl,
+                  void* stream);
+
+/* codes (N,K) uint8 row-major <-> native packed layout.  Replaces Quant3Linear.pack (quant.py:185-220). */
+int quip_pack_codes(const uint8_t* codes_nk, int32_t N, int32_t K, int32_t bits, int32_t* qweight,
+                    void* stream);
+int quip_unpack_codes(const int32_t* qweight, int32_t N, int32_t K, int32_t bits, uint8_t* codes_nk,
+                      void* stream);
+/* Reference layouts -> codes (N,K): bits=3 quant.py:192-220 [(K*3/32, N) int32], bits=4
+ * zeroShot/models/quant.py:193-199 [(K/8, N)], bits=2 the natural extension [(K/16, N)]. */
+int quip_convert_ref(const int32_t* ref_qweight, int32_t K, int32_t N, int32_t bits,
+                     uint8_t* codes_nk, void* stream);
+size_t quip_packed_words(int32_t N, int32_t K, int32_t bits);
+
+const char* quip_last_error(void);
+int quip_abi_version(void);
+/* Number of kernels this library has launched on behalf of the calling process (for bench gpu_launches). */
+int64_t quip_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUIP_B200_H_ */

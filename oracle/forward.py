@@ -76,8 +76,10 @@ def _r(a, on):
     return a.astype(f16).astype(f32) if on else a
 
 
-def kernel_plan(parts):
-    """Everything the packed module stores, derived from captured parts."""
+def kernel_plan(parts, fold=True):
+    """Everything the packed module stores, derived from captured parts.  `fold`: multiply 1/scaleWH
+    into the columns of the first V pass when every block has its own factor (what
+    quip_b200.incoherence.fold_inv_scale does), instead of scaling x in the gather."""
     bits = parts['bits']
     codes = parts['codes']
     N, K = codes.shape
@@ -95,6 +97,15 @@ def kernel_plan(parts):
     plan['P'], plan['R'] = qmath.kernel_affine(scales, zeros, bits)
     plan['inv_scale'] = None if parts.get('scaleWH') is None else (f32(1) / parts['scaleWH'].astype(f32))
     plan['bias'] = parts.get('bias')
+    if fold and plan['inv_scale'] is not None and plan['V'] is not None:
+        v = plan['V']
+        F, p, nblk, strided = v['passes'][0]
+        s = plan['inv_scale']
+        if F.shape[0] == nblk and s.max() / s.min() <= 1e3:
+            per_pos = s[v['io_idx']]
+            cols = per_pos.reshape(p, nblk).T if strided else per_pos.reshape(nblk, p)
+            v['passes'][0] = ((F * cols[:, None, :]).astype(f32), p, nblk, strided)
+            plan['inv_scale'] = None
     return plan
 
 

@@ -1,0 +1,175 @@
+// C-ABI entry points (include/quip_b200.h) and the launch sequence of one packed-linear forward.
+//
+//   y = ((x * inv_scale)[idx_V] -> V passes) . Q^T -> U passes -> [idx_U] + bias
+//
+// replaces Quant3Linear.forward -> quant_cuda.vecquant3matmul (reference quant.py:222-233) and the
+// un-projection the reference bakes into its dense weight (method.py:195-214).
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace quip {
+
+static thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// implemented in qgemm_skinny.cu / qgemm_tc.cu
+int qgemm_skinny(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M, int ksplit,
+                 float* part, int* counters, cudaStream_t s);
+int skinny_pick_ksplit(int N, int K, int rows_per_cta);
+size_t skinny_workspace_bytes(int N, int M, int ksplit);
+int qgemm_tc(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
+             cudaStream_t s);
+
+constexpr size_t WS_HEADER = 16 * 1024;     // split-K arrival counters; must be zero on first use, left zero
+constexpr int SKINNY_MAX_M = 32;
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct WsPlan {
+  size_t xsum, bufA, bufB, zbuf, bufC, part, total;
+};
+
+static bool side_on(const QuipSide& s) { return s.n > 0 && (s.npass > 0 || s.idx != nullptr); }
+
+static WsPlan plan_ws(const QuipLinearDesc* d, int64_t M) {
+  WsPlan p{};
+  size_t off = WS_HEADER;
+  p.xsum = off; off += align_up((size_t)M * sizeof(float), 256);
+  const bool v_on = side_on(d->V) || d->inv_scale;
+  const bool u_on = side_on(d->U);
+  size_t xk = align_up((size_t)M * d->K * sizeof(__half), 256);
+  size_t xn = align_up((size_t)M * d->N * sizeof(__half), 256);
+  p.bufA = off; if (v_on) off += xk;
+  p.bufB = off; if (v_on) off += xk;
+  p.zbuf = off; if (u_on) off += xn;
+  p.bufC = off; if (u_on) off += xn;
+  p.part = off;
+  if (M <= SKINNY_MAX_M) off += align_up(skinny_workspace_bytes(d->N, (int)M, skinny_pick_ksplit(d->N, d->K, 64)), 256);
+  p.total = off;
+  return p;
+}
+
+static int check_desc(const QuipLinearDesc* d) {
+  QUIP_CHECK_ARG(d != nullptr, "null descriptor");
+  QUIP_CHECK_ARG(d->bits >= 2 && d->bits <= 4, "bits must be 2, 3 or 4 (got %d)", d->bits);
+  QUIP_CHECK_ARG(d->K > 0 && d->K % 128 == 0, "K=%d must be a positive multiple of 128", d->K);
+  QUIP_CHECK_ARG(d->N > 0 && d->N % 16 == 0, "N=%d must be a positive multiple of 16", d->N);
+  QUIP_CHECK_ARG(d->qweight && d->scales && d->zeros, "qweight / scales / zeros must be set");
+  QUIP_CHECK_ARG(d->V.n == 0 || d->V.n == d->K, "V side size %d != K %d", d->V.n, d->K);
+  QUIP_CHECK_ARG(d->U.n == 0 || d->U.n == d->N, "U side size %d != N %d", d->U.n, d->N);
+  QUIP_CHECK_ARG(d->V.npass >= 0 && d->V.npass <= 2 && d->U.npass >= 0 && d->U.npass <= 2, "npass must be 0..2");
+  return QUIP_OK;
+}
+
+static int run_qgemm(const QuipLinearDesc* d, const __half* x2, const float* xsum, const __half* bias, __half* z,
+                     int64_t M, int path, unsigned char* ws, const WsPlan& p, cudaStream_t s) {
+  if (path == 0) path = M <= SKINNY_MAX_M ? 1 : 2;
+  if (path == 1) {
+    // the skinny kernel takes <= 32 tokens per launch and sums x itself
+    for (int64_t m0 = 0; m0 < M; m0 += SKINNY_MAX_M) {
+      int mc = (int)((M - m0) < SKINNY_MAX_M ? (M - m0) : SKINNY_MAX_M);
+      int ksplit = M <= SKINNY_MAX_M ? skinny_pick_ksplit(d->N, d->K, 64) : 1;
+      if (int e = qgemm_skinny(d, x2 + m0 * d->K, bias, z + m0 * d->N, mc, ksplit,
+                               reinterpret_cast<float*>(ws + p.part), reinterpret_cast<int*>(ws), s))
+        return e;
+    }
+    return QUIP_OK;
+  }
+  const bool need_xsum = !(d->flags & QUIP_FLAG_SYMMETRIC);
+  QUIP_CHECK_ARG(!need_xsum || xsum, "asymmetric grid needs the row sums of x");
+  return qgemm_tc(d, x2, xsum, bias, z, (int)M, s);
+}
+
+}  // namespace quip
+
+using namespace quip;
+
+extern "C" const char* quip_last_error(void) { return g_err; }
+extern "C" int quip_abi_version(void) { return QUIP_ABI_VERSION; }
+extern "C" int64_t quip_launch_count(void) { return g_launches.load(); }
+
+extern "C" int quip_qlinear_workspace_bytes(const QuipLinearDesc* d, int64_t M, size_t* out) {
+  if (int e = check_desc(d)) return e;
+  QUIP_CHECK_ARG(out && M > 0, "bad arguments");
+  *out = plan_ws(d, M).total;
+  return QUIP_OK;
+}
+
+extern "C" int quip_qgemm(const QuipLinearDesc* d, const void* x2, const float* xsum, const void* bias, void* z,
+                          int64_t M, int path, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int e = check_desc(d)) return e;
+  QUIP_CHECK_ARG(x2 && z && M > 0 && M < (1ll << 31), "bad arguments");
+  WsPlan p = plan_ws(d, M);
+  QUIP_CHECK_ARG(path >= 0 && path <= 2, "path must be 0, 1 or 2");
+  if ((path == 1 || (path == 0 && M <= SKINNY_MAX_M)) && M <= SKINNY_MAX_M) {
+    if (!workspace || workspace_bytes < p.total) {
+      set_error("workspace too small: need %zu bytes, have %zu", p.total, workspace_bytes);
+      return QUIP_ERR_WORKSPACE;
+    }
+  }
+  return run_qgemm(d, (const __half*)x2, xsum, (const __half*)bias, (__half*)z, M, path, (unsigned char*)workspace, p,
+                   (cudaStream_t)stream);
+}
+
+extern "C" int quip_qlinear_forward(const QuipLinearDesc* d, const void* x_, void* y_, int64_t M, void* workspace,
+                                    size_t workspace_bytes, void* stream) {
+  if (int e = check_desc(d)) return e;
+  QUIP_CHECK_ARG(x_ && y_ && M > 0 && M < (1ll << 31), "bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  WsPlan p = plan_ws(d, M);
+  if (!workspace || workspace_bytes < p.total) {
+    set_error("workspace too small: need %zu bytes, have %zu", p.total, workspace_bytes);
+    return QUIP_ERR_WORKSPACE;
+  }
+  unsigned char* ws = (unsigned char*)workspace;
+  const __half* x = (const __half*)x_;
+  __half* y = (__half*)y_;
+  __half* bufA = (__half*)(ws + p.bufA);
+  __half* bufB = (__half*)(ws + p.bufB);
+  __half* zbuf = (__half*)(ws + p.zbuf);
+  __half* bufC = (__half*)(ws + p.bufC);
+  float* xsum = (float*)(ws + p.xsum);
+  const int K = d->K, N = d->N;
+
+  // ---- K side: x2 = passes( (x * inv_scale)[idx] ) ----
+  const __half* cur = x;
+  if (d->V.idx || d->inv_scale) {
+    if (int e = quip_gather(cur, bufA, M, K, d->V.n ? d->V.idx : nullptr, d->inv_scale, nullptr, stream)) return e;
+    cur = bufA;
+  }
+  for (int i = 0; i < (d->V.n ? d->V.npass : 0); ++i) {
+    __half* dst = (cur == bufA) ? bufB : bufA;
+    if (int e = quip_rot_pass(&d->V.pass[i], cur, dst, M, K, 0, stream)) return e;
+    cur = dst;
+  }
+  const __half* x2 = cur;
+
+  // ---- contraction with the packed matrix ----
+  const bool u_on = side_on(d->U);
+  const bool need_xsum = !(d->flags & QUIP_FLAG_SYMMETRIC) && M > SKINNY_MAX_M;
+  if (need_xsum)
+    if (int e = quip_rowsum(x2, xsum, M, K, stream)) return e;
+  __half* zdst = u_on ? zbuf : y;
+  if (int e = run_qgemm(d, x2, xsum, u_on ? nullptr : (const __half*)d->bias, zdst, M, 0, ws, p, s)) return e;
+  if (!u_on) return QUIP_OK;
+
+  // ---- N side: y = passes(z)[idx] + bias ----
+  const __half* zc = zbuf;
+  const int np = d->U.npass;
+  const bool tail_gather = d->U.idx || d->bias;
+  for (int i = 0; i < np; ++i) {
+    __half* dst = (i == np - 1 && !tail_gather) ? y : ((zc == zbuf) ? bufC : zbuf);
+    if (int e = quip_rot_pass(&d->U.pass[i], zc, dst, M, N, 0, stream)) return e;
+    zc = dst;
+  }
+  if (tail_gather) return quip_gather(zc, y, M, N, d->U.idx, nullptr, d->bias, stream);
+  return QUIP_OK;
+}

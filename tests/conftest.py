@@ -39,3 +39,51 @@ def load_layer(name):
 
 LAYER_NAMES = ['l2b_incoh', 'l2b_incoh_rg', 'l3b_incoh', 'l4b_plain', 'l2b_kron', 'l4b_noperm',
                'l3b_rescale', 'l2b_qfna_proj']
+
+
+def parts_to_torch(parts):
+    """numpy `parts` dict (load_layer) -> quip_b200.capture.LayerParts."""
+    import torch
+    from quip_b200.capture import Butterfly, LayerParts
+
+    def bfly(b, n):
+        if b is None:
+            return None
+        (B, p_in, p_out) = b
+        return Butterfly(n, torch.from_numpy(B[0]).float(), torch.from_numpy(B[1]).float(),
+                         torch.from_numpy(p_in).long(), torch.from_numpy(p_out).long())
+    N, K = parts['codes'].shape
+    return LayerParts(bits=parts['bits'], qfn=parts['qfn'], codes=torch.from_numpy(parts['codes']),
+                      scales=torch.from_numpy(parts['scales']), zeros=torch.from_numpy(parts['zeros']),
+                      bias=None if parts['bias'] is None else torch.from_numpy(parts['bias']),
+                      scaleWH=None if parts['scaleWH'] is None else torch.from_numpy(parts['scaleWH']),
+                      U=bfly(parts['U'], N), V=bfly(parts['V'], K))
+
+
+def load_tiny_opt():
+    """Tiny OPT fixture quantized + evaluated by the live reference (oracle/gen_golden_models.py).
+    Returns (dense fp16 model as the reference left it, {layer name: LayerParts}, test ids, reference ppl)."""
+    import ast
+    import numpy as np
+    import torch
+    from transformers import OPTConfig
+    from quip_b200.capture import Butterfly, LayerParts
+    from quip_b200.opt import get_opt
+    z = np.load(os.path.join(GOLDEN, 'tiny_opt_2bit_incoh.npz'))
+    cfg = OPTConfig(**ast.literal_eval(str(z['config'])))
+    model = get_opt(cfg)
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith('sd/')}
+    model.load_state_dict(sd)
+    parts = {}
+    for name in [str(n) for n in z['names']]:
+        p = 'parts/' + name + '/'
+        N, K = z[p + 'codes'].shape
+
+        def bf(side, n):
+            return Butterfly(n, torch.from_numpy(z[p + side + '_B0']), torch.from_numpy(z[p + side + '_B1']),
+                             torch.from_numpy(z[p + side + '_p_in']), torch.from_numpy(z[p + side + '_p_out']))
+        parts[name] = LayerParts(bits=2, qfn='b', codes=torch.from_numpy(z[p + 'codes']),
+                                 scales=torch.from_numpy(z[p + 'scales']), zeros=torch.from_numpy(z[p + 'zeros']),
+                                 bias=torch.from_numpy(z[p + 'bias']) if (p + 'bias') in z.files else None,
+                                 scaleWH=torch.from_numpy(z[p + 'scaleWH']), U=bf('U', N), V=bf('V', K))
+    return model, parts, torch.from_numpy(z['test_ids']), float(z['ppl'])

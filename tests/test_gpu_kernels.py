@@ -1,0 +1,129 @@
+"""CUDA kernels vs the CPU oracle, through the C ABI.  Everything except the tcgen05 GEMM (which has
+its own file so a protocol bug there cannot poison this process's CUDA context)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import butterfly as obf
+from oracle import forward as ofw
+from oracle import packing as opk
+from oracle import qmath
+
+pytestmark = pytest.mark.gpu
+
+f16, f32 = np.float16, np.float32
+
+
+def _rel(a, b):
+    return ofw.rel_err(a, b)
+
+
+@pytest.mark.parametrize('bits', [2, 3, 4])
+@pytest.mark.parametrize('shape', [(16, 128), (48, 384), (4096, 4096), (176, 11008)])
+def test_gpu_packer_bit_exact(bits, shape):
+    from quip_b200 import quant as Q
+    rng = np.random.default_rng(bits + shape[0])
+    codes = rng.integers(0, 1 << bits, size=shape, dtype=np.uint8)
+    q = Q.pack_codes(torch.from_numpy(codes).cuda(), bits)
+    want = opk.native_pack(codes, bits)
+    np.testing.assert_array_equal(q.cpu().numpy(), want)
+    back = Q.unpack_codes(q, *shape, bits)
+    np.testing.assert_array_equal(back.cpu().numpy(), codes)
+
+
+def test_reference_layouts_decode_on_gpu():
+    from quip_b200 import quant as Q
+    z = np.load(os.path.join(GOLDEN, 'packing_ref.npz'))
+    for bits in (3, 4):
+        codes = z[f'codes{bits}']
+        N, K = codes.shape
+        got = Q.convert_ref_qweight(torch.from_numpy(z[f'qweight{bits}']).cuda(), K, N, bits)
+        np.testing.assert_array_equal(got.cpu().numpy(), codes)
+    rng = np.random.default_rng(0)
+    codes = rng.integers(0, 4, size=(32, 256), dtype=np.uint8)
+    got = Q.convert_ref_qweight(torch.from_numpy(opk.ref_pack2(codes)).cuda(), 256, 32, 2)
+    np.testing.assert_array_equal(got.cpu().numpy(), codes)
+
+
+@pytest.mark.parametrize('M,n', [(1, 128), (5, 384), (64, 11008)])
+def test_gather_scale_bias(M, n):
+    from gpu_util import run_gather
+    rng = np.random.default_rng(n)
+    X = rng.standard_normal((M, n)).astype(f16)
+    idx = rng.permutation(n)
+    scale = (0.5 + rng.random(n)).astype(f32)
+    bias = rng.standard_normal(n).astype(f16)
+    got = run_gather(X, idx, scale, bias)
+    want = (X.astype(np.float64)[:, idx] * scale[idx][None, :] + bias.astype(np.float64)[None, :])
+    # the kernel contracts scale and bias with one fp32 FMA before the fp16 rounding: <= 1 ulp from this
+    np.testing.assert_allclose(got.astype(np.float64), want, rtol=1.5e-3, atol=1e-6)
+    np.testing.assert_array_equal(run_gather(X, idx), X[:, idx])
+    np.testing.assert_array_equal(run_gather(X, None, scale), (X.astype(f32) * scale[None, :]).astype(f16))
+
+
+PASS_CASES = [
+    # p, nblk, strided, shared
+    (16, 16, False, False), (16, 16, True, False), (24, 16, True, False), (16, 24, False, False),
+    (40, 16, False, False), (16, 40, True, False), (8, 16, True, False), (16, 8, False, False),
+    (64, 64, False, False), (64, 64, True, False), (64, 32, True, False), (32, 64, False, False),
+    (48, 16, False, False), (16, 48, True, False), (64, 64, True, True), (64, 64, False, True),
+    (688, 16, False, False), (16, 688, True, False), (224, 32, False, False), (96, 32, False, False),
+    (128, 64, False, True), (43, 16, False, False), (16, 43, True, False), (7, 9, True, False),
+]
+
+
+@pytest.mark.parametrize('p,nblk,strided,shared', PASS_CASES)
+@pytest.mark.parametrize('M', [1, 37, 300])
+def test_rot_pass_vs_oracle(p, nblk, strided, shared, M):
+    from gpu_util import run_pass
+    n = p * nblk
+    rng = np.random.default_rng(p * 1000 + nblk + M)
+    X = rng.standard_normal((M, n)).astype(f16)
+    F = (rng.standard_normal((1 if shared else nblk, p, p)) / np.sqrt(p)).astype(f16)
+    want = obf.apply_pass(X.astype(np.float64), F.astype(np.float64), p, nblk, strided)
+    got = run_pass(X, F, p, nblk, strided, impl=0)
+    assert got.shape == want.shape
+    assert _rel(got, want) < 4e-4, (p, nblk, strided, shared, M)
+    # the tensor-core kernels and the generic CUDA-core kernel agree (same fp16 output rounding)
+    simple = run_pass(X, F, p, nblk, strided, impl=1)
+    assert _rel(simple, want) < 4e-4
+    assert _rel(got, simple) < 3e-4
+
+
+def _qgemm_case(bits, N, K, M, symmetric, seed):
+    rng = np.random.default_rng(seed)
+    codes = rng.integers(0, 1 << bits, size=(N, K), dtype=np.uint8)
+    scales = (0.01 + 0.02 * rng.random((N, 1))).astype(f32)
+    cbar = ((1 << bits) - 1) / 2
+    if symmetric:
+        zeros = (scales * f32(cbar)).astype(f32)
+    else:
+        zeros = (scales * rng.integers(0, 1 << bits, size=(N, 1)).astype(f32)).astype(f32)
+    X = (rng.standard_normal((M, K)) * (1 + 3 * rng.random(K))[None, :]).astype(f16)
+    bias = rng.standard_normal(N).astype(f16)
+    Qm = scales.astype(np.float64) * codes.astype(np.float64) - zeros.astype(np.float64)
+    want = X.astype(np.float64) @ Qm.T + bias.astype(np.float64)[None, :]
+    return codes, scales, zeros, X, bias, want
+
+
+@pytest.mark.parametrize('bits', [2, 3, 4])
+@pytest.mark.parametrize('M', [1, 3, 8, 9, 16, 17, 32])
+@pytest.mark.parametrize('symmetric', [True, False])
+def test_qgemm_skinny_vs_oracle(bits, M, symmetric):
+    from gpu_util import run_qgemm
+    for (N, K) in [(64, 128), (48, 384), (256, 1024), (4096, 4096)]:
+        codes, scales, zeros, X, bias, want = _qgemm_case(bits, N, K, M, symmetric, bits * 100 + M)
+        z, xsum = run_qgemm(codes, scales, zeros, bits, X, path=1, bias=bias, symmetric=symmetric)
+        np.testing.assert_allclose(xsum, X.astype(np.float64).sum(1), rtol=1e-4, atol=1e-2)
+        assert not np.isnan(z.astype(f32)).any()
+        assert _rel(z, want) < 3e-4, (bits, M, symmetric, N, K, _rel(z, want))
+
+
+def test_qgemm_skinny_large_M_loops():
+    from gpu_util import run_qgemm
+    codes, scales, zeros, X, bias, want = _qgemm_case(2, 256, 512, 100, False, 5)
+    z, _ = run_qgemm(codes, scales, zeros, 2, X, path=1, bias=bias, symmetric=False)
+    assert _rel(z, want) < 3e-4

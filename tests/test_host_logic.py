@@ -1,0 +1,156 @@
+"""Host-side logic and the C-ABI surface, CPU only (no compute calls into the CUDA library)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from conftest import GOLDEN, LAYER_NAMES, ROOT, load_layer, parts_to_torch
+from oracle import butterfly as obf
+from oracle import forward as ofw
+from oracle import packing as opk
+from quip_b200 import _lib
+from quip_b200 import quant as Q
+from quip_b200.incoherence import plan_side
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, 'include', 'quip_b200.h')).read()
+    declared = set(re.findall(r'\b(quip_[a-z_0-9]+)\s*\(', header))
+    assert declared, 'no declarations parsed'
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/quip_b200.h but not exported'
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    assert lib.quip_abi_version() == 1
+    assert lib.quip_packed_words(16, 128, 2) == 128
+    assert lib.quip_packed_words(16, 128, 3) == 192
+    assert lib.quip_packed_words(16, 100, 2) == 0          # bad shape -> 0
+
+
+def test_argument_errors_surface_as_messages():
+    lib = _lib.load()
+    rc = lib.quip_pack_codes(None, 16, 100, 2, None, None)   # K % 128 != 0: rejected before any CUDA call
+    assert rc == 1
+    assert b'multiple of 128' in lib.quip_last_error()
+    with pytest.raises(_lib.QuipError):
+        _lib.check(rc)
+
+
+@pytest.mark.parametrize('bits', [2, 3, 4])
+def test_host_packer_matches_oracle_layout(bits):
+    rng = np.random.default_rng(bits)
+    codes = rng.integers(0, 1 << bits, size=(48, 384), dtype=np.uint8)
+    q = Q.pack_codes(torch.from_numpy(codes), bits)
+    np.testing.assert_array_equal(q.numpy(), opk.native_pack(codes, bits))
+    np.testing.assert_array_equal(Q.unpack_codes(q, 48, 384, bits).numpy(), codes)
+    with pytest.raises(ValueError):
+        Q.packed_words(20, 384, bits)
+
+
+def test_quantizer_matches_reference_outputs():
+    z = np.load(os.path.join(GOLDEN, 'quantizer.npz'))
+    for bits in (2, 3, 4):
+        w = torch.from_numpy(z[f'w{bits}'])
+        qz = Q.Quantizer()
+        qz.configure(bits, perchannel=True, sym=False, qfn='a', mse=False)
+        assert not qz.ready()
+        qz.find_params(w, weight=True)
+        assert qz.ready() and qz.enabled()
+        np.testing.assert_array_equal(qz.scale.numpy(), z[f'scale{bits}'])
+        np.testing.assert_array_equal(qz.zero.numpy(), z[f'zero{bits}'])
+        np.testing.assert_array_equal(qz.quantize(w).numpy(), z[f'qa{bits}'])
+        qb = Q.Quantizer()
+        qb.configure(bits, perchannel=True, sym=False, qfn='b', mse=False)
+        qb.find_params(w, weight=True)
+        assert qb.scale is None                      # quant.py:138-142
+        np.testing.assert_array_equal(qb.quantize(w).numpy(), z[f'qb{bits}'])
+        np.testing.assert_array_equal(qb.scale.numpy(), z[f'sb{bits}'])
+
+
+@pytest.mark.parametrize('name', [n for n in LAYER_NAMES if n not in ('l4b_plain', 'l3b_rescale')])
+def test_side_plans_match_oracle(name):
+    parts, _ = load_layer(name)
+    tp = parts_to_torch(parts)
+    for side, bfly, n in (('V', tp.V, tp.codes.shape[1]), ('U', tp.U, tp.codes.shape[0])):
+        plan = plan_side(bfly, side)
+        ref = obf.side_plan(parts[side], n, side)
+        assert plan.layout == ref['layout']
+        np.testing.assert_array_equal(plan.order.numpy(), ref['order'])
+        want_idx = ref['io_idx'] if side == 'V' else np.argsort(ref['io_idx'])
+        got_idx = np.arange(n) if plan.idx is None else plan.idx.numpy()
+        np.testing.assert_array_equal(got_idx, want_idx)
+        for ps, (F, p, nblk, strided) in zip(plan.passes, ref['passes']):
+            assert (ps.p, ps.nblk, ps.strided) == (p, nblk, strided)
+            np.testing.assert_array_equal(ps.factors.numpy(), F)
+
+
+@pytest.mark.parametrize('name', LAYER_NAMES)
+def test_quantlinear_pack_parts_and_state_dict(name):
+    parts, z = load_layer(name)
+    tp = parts_to_torch(parts)
+    N, K = tp.codes.shape
+    spec = Q.spec_from_parts(tp)
+    ql = Q.QuantLinear(infeatures=K, outfeatures=N, **spec)
+    ql.pack_parts(tp)
+    # integer codes: bit-exact against the reference's, under the known layout permutation
+    plan = ofw.kernel_plan(parts)
+    np.testing.assert_array_equal(ql.codes().numpy(), plan['codes'])
+    np.testing.assert_array_equal(ql.qweight.numpy(), opk.native_pack(plan['codes'], parts['bits']))
+    assert bool(ql.meta[1]) == (parts['qfn'] == 'b')
+    # state_dict round trip into a freshly constructed module
+    ql2 = Q.QuantLinear(infeatures=K, outfeatures=N, **spec)
+    ql2.load_state_dict(ql.state_dict())
+    for k, v in ql.state_dict().items():
+        assert torch.equal(v, ql2.state_dict()[k]), k
+    with pytest.raises(RuntimeError):
+        ql(torch.zeros(1, K, dtype=torch.float16))         # no CPU path
+    with pytest.raises(ValueError):
+        ql(torch.zeros(1, K + 1, dtype=torch.float16))
+
+
+def test_pack_reference_contract_qfna():
+    """Quant3Linear.pack contract (quant.py:185-191): grid weights + quantizer scale/zero -> codes."""
+    parts, z = load_layer('l4b_plain')
+    N, K = parts['codes'].shape
+    lin = nn.Linear(K, N)
+    lin.weight.data = torch.from_numpy(z['W_ref']).float()          # no incoherence: W_ref is the grid itself
+    lin.bias.data = torch.from_numpy(parts['bias']).float()
+    ql = Q.QuantLinear(4, K, N, bias=True)
+    ql.pack(lin, torch.from_numpy(z['raw_scale']), torch.from_numpy(z['raw_zero']))
+    np.testing.assert_array_equal(ql.codes().numpy(), parts['codes'])
+    np.testing.assert_allclose(ql.zeros.numpy(), z['raw_zero'] * z['raw_scale'])
+    bad = nn.Linear(K, N)
+    with pytest.raises(ValueError):
+        Q.QuantLinear(4, K, N, incoh='blocked').pack(bad, torch.ones(N, 1), torch.zeros(N, 1))
+
+
+def test_make_quant_swaps_exactly_the_named_layers():
+    class Block(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.q_proj = nn.Linear(128, 128)
+            self.fc1 = nn.Linear(128, 256, bias=False)
+            self.keep = nn.Linear(128, 128)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.layers = nn.ModuleList([Block(), Block()])
+            self.lm_head = nn.Linear(128, 512)
+
+    net = Net()
+    names = ['layers.0.q_proj', 'layers.1.fc1']
+    Q.make_quant(net, names, bits=2)
+    assert isinstance(net.layers[0].q_proj, Q.QuantLinear) and net.layers[0].q_proj.bias is not None
+    assert isinstance(net.layers[1].fc1, Q.QuantLinear) and net.layers[1].fc1.bias is None
+    assert type(net.layers[0].fc1) is nn.Linear and type(net.layers[1].q_proj) is nn.Linear
+    assert type(net.layers[0].keep) is nn.Linear and type(net.lm_head) is nn.Linear
+    assert net.layers[1].fc1.infeatures == 128 and net.layers[1].fc1.outfeatures == 256
+    Q.make_quant(net, names, bits=2)                           # idempotent on already-swapped modules
+    Q.make_quant3(net, ['layers.0.keep'])
+    assert net.layers[0].keep.bits == 3
+    with pytest.raises(NotImplementedError):
+        Q.QuantLinear(8, 128, 128)
