@@ -1,0 +1,251 @@
+"""bench.py -- tokens/s of the packed 2-bit Llama-2-7B eval path on N B200s (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2], the config `metric` is quoted on): Llama-2-7B architecture, every
+decoder Linear a 2-bit packed QuantLinear with the as-run blocked incoherence butterflies + rescale
+(`--incoh_processing`), synthetic 2048-token samples, random-init weights / random codes (no network).
+A *step* = one 2048-token sample through the per-layer eval path (embed -> 32 decoder layers, 7 packed
+linears each -> final norm -> lm_head -> CE loss), i.e. one pass of llama_eval's inner loop.
+
+  value   whole-job tokens/s with token ids already resident in HBM (CUDA events, barrier + sync on both
+          sides, max over ranks).  Data parallel over samples: each rank runs K steps (weak scaling); the
+          path's only collective, one all-reduce of the summed NLL, is inside the timed region.
+  e2e     the same metric through the public API quip_b200.llama.llama_eval with HOST token ids: every step
+          copies its ids from pinned host memory and reads the scalar result back.
+  roofline  the dominant kernel (tcgen05 packed GEMM): algorithmic flops of its launches / their summed
+          device time, measured with CUDA events around every launch inside the timed region.
+  cpu_baseline / --impl reference: the reference's effective path (HF decoder layer with dense fp16
+          weights, the per-layer loop of llama.py:174-253 ported in oracle/evalloop.py) on the host cores,
+          on a bounded sample (1 decoder layer x 1 sample), extrapolated to 32 layers.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SEQ = 2048
+N_LAYERS = 32
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm_gbs=d['hbm_gbs'], tflops_burst=d['bf16_tflops'], tflops_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm_gbs=6650.0, tflops_burst=1590.0, tflops_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()        # exact PID we started
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        return False
+
+    def summary(self):
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith('active') for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2], sm_max_mhz=float(self.rows[0][1]), reasons=reasons, samples=len(sm),
+                    power_w_max=max(float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace('.', '').isdigit()))
+
+
+def cpu_reference_arm(steps, warmup):
+    """The reference's own implementation of the path on the host cores: dense fp16 decoder layer through
+    the reference loop (oracle/evalloop.py).  Bounded sample: ONE decoder layer x ONE 2048-token sample per
+    step; tokens/s extrapolated to the 32-layer stack (attention, norms and MLP included; embedding and
+    lm_head excluded, as they are not on the quantized path)."""
+    from transformers import LlamaConfig
+    from oracle.evalloop import reference_eval
+    from quip_b200.llama import get_llama
+    from quip_b200.synth import LLAMA2_7B
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    cfg = LlamaConfig(**{**LLAMA2_7B, 'num_hidden_layers': 1})
+    model = get_llama(cfg, seqlen=SEQ)
+    ids = torch.randint(0, cfg.vocab_size, (1, SEQ), generator=torch.Generator().manual_seed(0))
+    times = []
+    for i in range(warmup + steps):
+        timing = {}
+        reference_eval(model, ids, nlayers=1, timing=timing)
+        if i >= warmup:
+            times.append(timing['layer_loop_s'])
+    per_layer = sum(times) / len(times)
+    value = SEQ / (per_layer * N_LAYERS)
+    sample = (f'1 decoder layer x 1 sample of {SEQ} tokens per step (dense fp16 nn.Linear on CPU, {cores} threads), '
+              f'{per_layer:.3f} s/layer, extrapolated x{N_LAYERS} layers')
+    return value, per_layer, cores, sample
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=8)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--layers', type=int, default=N_LAYERS, help=argparse.SUPPRESS)   # debugging only
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    base = dict(metric='tokens/sec 2-bit Llama-2-7B (per-layer eval path, seq 2048)', unit='tokens/s', n_gpus=a.gpus,
+                steps=a.steps, warmup=a.warmup, higher_is_better=True, scaling='weak', vs_baseline=None, data='synthetic',
+                config=dict(workload='Llama-2-7B 2-bit --incoh_processing (blocked butterflies + rescale), seq 2048, batch 1 '
+                                     'per step, random codes / random orthogonal factors / random-init embeddings',
+                            parallelism=f'dp{a.gpus}', l2='inputs larger than L2: each step streams 3.5 GB of packed '
+                                                          'weights + butterfly factors'))
+
+    if a.impl == 'reference':
+        if rank != 0:
+            return
+        value, per_layer, cores, sample = cpu_reference_arm(max(1, min(a.steps, 3)), 1)
+        out = dict(base, impl='reference', value=value, ms_per_step=per_layer * N_LAYERS * 1e3, dtype='f16',
+                   cpu_baseline=dict(value=value, unit='tokens/s', cores=cores, kind='port', sample=sample),
+                   e2e=dict(value=value, unit='tokens/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+        print(json.dumps(out))
+        return
+
+    assert a.warmup >= 3, 'timing rules: at least 3 warm-up steps'
+    from transformers import LlamaConfig
+    from quip_b200 import _lib, evalloop, pipeline
+    from quip_b200.llama import llama_eval
+    from quip_b200.synth import LLAMA2_7B, build_synthetic_model
+    pipeline.init_distributed()
+    import torch.distributed as dist
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    lib = _lib.load()
+
+    cfg = LlamaConfig(**{**LLAMA2_7B, 'num_hidden_layers': a.layers})
+    model = build_synthetic_model(cfg, dev, bits=2, incoh='blocked', rescale=True, seed=rank, seqlen=SEQ)
+    gen = torch.Generator().manual_seed(1234 + rank)
+    total = a.warmup + a.steps
+    ids_host = torch.randint(0, cfg.vocab_size, (total, 1, SEQ), generator=gen).pin_memory()
+    ids_dev = ids_host.to(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t[0])
+        return ms
+
+    # ---- device-resident timing ----
+    with torch.no_grad():
+        for i in range(a.warmup):
+            evalloop.sample_nll(model, evalloop.LLAMA, ids_dev[i])
+        barrier()
+        lib.quip_timing_reset()
+        lib.quip_timing_enable(1)
+        launches0 = lib.quip_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with ClockSampler(local) as clk:
+            barrier()
+            e0.record()
+            nll = torch.zeros((), device=dev)
+            for i in range(a.warmup, total):
+                nll += evalloop.sample_nll(model, evalloop.LLAMA, ids_dev[i])
+            if world > 1:
+                dist.all_reduce(nll)
+            e1.record()
+            barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        launches = lib.quip_launch_count() - launches0
+        lib.quip_timing_enable(0)
+        tms, tn, tfl, tby = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
+        _lib.check(lib.quip_timing_read(2, C.byref(tms), C.byref(tn), C.byref(tfl), C.byref(tby)))
+        lib.quip_timing_reset()
+
+        # ---- end to end through the public API, host token ids ----
+        for i in range(2):
+            llama_eval(model, ids_host[i], dev, verbose=False)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(a.warmup, total):
+            llama_eval(model, ids_host[i], dev, verbose=False)      # H2D of the ids, D2H of the ppl scalar inside
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        e2e_ms = max_over_ranks(e2e_s * 1e3)
+
+    if world > 1:
+        t = torch.tensor([float(launches)], device=dev)
+        dist.all_reduce(t)
+        launches = int(t[0])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    value = world * a.steps * SEQ / (ms / 1e3)
+    e2e_value = world * a.steps * SEQ / (e2e_ms / 1e3)
+    achieved = tfl.value / (tms.value / 1e3) / 1e12 if tms.value > 0 else None
+    traffic = None
+    prof = os.path.join(ROOT, 'profiles', 'ncu_qgemm_tc_latest.json')
+    if os.path.exists(prof):
+        traffic = json.load(open(prof)).get('dram_bytes_per_launch')
+    out = dict(base, value=value, ms_per_step=ms / a.steps, dtype='f16', impl='ours', gpu_launches=int(launches),
+               e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=SEQ * 8, d2h_bytes_per_step=4,
+                        api='quip_b200.llama.llama_eval'),
+               roofline=dict(bound='tensor', kernel='qgemm_tc_kernel<2,256> (tcgen05 packed GEMM)', achieved=achieved,
+                             peak=pk['tflops_sustained'], unit='TFLOP/s', frac=(achieved / pk['tflops_sustained']) if achieved else None,
+                             traffic=traffic, launches_timed=int(tn.value), kernel_ms_per_step=tms.value / a.steps,
+                             share_of_step=tms.value / ms, peak_source=pk['source'] + ', sustained bf16 (kernel timed inside a long step)'),
+               clocks=clk.summary())
+    if world == 1 and not a.no_cpu_baseline:
+        v, per_layer, cores, sample = cpu_reference_arm(1, 1)
+        out['cpu_baseline'] = dict(value=v, unit='tokens/s', cores=cores, kind='port', sample=sample)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

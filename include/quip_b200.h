@@ -116,6 +116,14 @@ int quip_convert_ref(const int32_t* ref_qweight, int32_t K, int32_t N, int32_t b
                      uint8_t* codes_nk, void* stream);
 size_t quip_packed_words(int32_t N, int32_t K, int32_t bits);
 
+/* Optional per-launch timing of the contraction kernels with CUDA events recorded on the launch stream
+ * (bench.py's roofline leg).  path: 1 = mma.sync skinny kernel, 2 = tcgen05 kernel.  quip_timing_read
+ * waits for the recorded events and returns the totals since the last reset: device milliseconds,
+ * launches, algorithmic flops (2*M*N*K) and algorithmic bytes (packed codes + fp16 activations in + out). */
+int quip_timing_enable(int on);
+int quip_timing_reset(void);
+int quip_timing_read(int path, double* total_ms, int64_t* launches, double* flops, double* bytes);
+
 const char* quip_last_error(void);
 int quip_abi_version(void);
 /* Number of kernels this library has launched on behalf of the calling process (for bench gpu_launches). */

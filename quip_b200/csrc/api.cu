@@ -6,6 +6,8 @@
 // un-projection the reference bakes into its dense weight (method.py:195-214).
 #include <stdarg.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace quip {
@@ -69,9 +71,44 @@ static int check_desc(const QuipLinearDesc* d) {
   return QUIP_OK;
 }
 
+// ---- optional event timing of the contraction kernels (bench.py roofline leg) ----
+struct TimedLaunch {
+  cudaEvent_t e0, e1;
+  int path;
+  double flops, bytes;
+};
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;      // recorded launches since the last reset
+static std::vector<TimedLaunch> g_pool;       // event pairs available for reuse
+constexpr size_t TIMED_MAX = 1 << 16;
+
+static int run_qgemm_untimed(const QuipLinearDesc* d, const __half* x2, const float* xsum, const __half* bias,
+                             __half* z, int64_t M, int path, unsigned char* ws, const WsPlan& p, cudaStream_t s);
+
 static int run_qgemm(const QuipLinearDesc* d, const __half* x2, const float* xsum, const __half* bias, __half* z,
                      int64_t M, int path, unsigned char* ws, const WsPlan& p, cudaStream_t s) {
   if (path == 0) path = M <= SKINNY_MAX_M ? 1 : 2;
+  if (!g_timing || g_timed.size() >= TIMED_MAX) return run_qgemm_untimed(d, x2, xsum, bias, z, M, path, ws, p, s);
+  TimedLaunch t;
+  if (!g_pool.empty()) {
+    t = g_pool.back();
+    g_pool.pop_back();
+  } else {
+    QUIP_CUDA(cudaEventCreate(&t.e0));
+    QUIP_CUDA(cudaEventCreate(&t.e1));
+  }
+  t.path = path;
+  t.flops = 2.0 * (double)M * d->N * d->K;
+  t.bytes = (double)d->N * d->K * d->bits / 8.0 + 2.0 * (double)M * (d->K + d->N);
+  QUIP_CUDA(cudaEventRecord(t.e0, s));
+  int e = run_qgemm_untimed(d, x2, xsum, bias, z, M, path, ws, p, s);
+  QUIP_CUDA(cudaEventRecord(t.e1, s));
+  g_timed.push_back(t);
+  return e;
+}
+
+static int run_qgemm_untimed(const QuipLinearDesc* d, const __half* x2, const float* xsum, const __half* bias,
+                             __half* z, int64_t M, int path, unsigned char* ws, const WsPlan& p, cudaStream_t s) {
   if (path == 1) {
     // the skinny kernel takes <= 32 tokens per launch and sums x itself
     for (int64_t m0 = 0; m0 < M; m0 += SKINNY_MAX_M) {
@@ -95,6 +132,32 @@ using namespace quip;
 extern "C" const char* quip_last_error(void) { return g_err; }
 extern "C" int quip_abi_version(void) { return QUIP_ABI_VERSION; }
 extern "C" int64_t quip_launch_count(void) { return g_launches.load(); }
+
+extern "C" int quip_timing_enable(int on) {
+  g_timing = on != 0;
+  return QUIP_OK;
+}
+extern "C" int quip_timing_reset(void) {
+  for (auto& t : g_timed) g_pool.push_back(t);
+  g_timed.clear();
+  return QUIP_OK;
+}
+extern "C" int quip_timing_read(int path, double* total_ms, int64_t* launches, double* flops, double* bytes) {
+  double ms = 0, fl = 0, by = 0;
+  int64_t n = 0;
+  for (auto& t : g_timed) {
+    if (t.path != path) continue;
+    QUIP_CUDA(cudaEventSynchronize(t.e1));
+    float dt = 0.f;
+    QUIP_CUDA(cudaEventElapsedTime(&dt, t.e0, t.e1));
+    ms += dt; fl += t.flops; by += t.bytes; ++n;
+  }
+  if (total_ms) *total_ms = ms;
+  if (launches) *launches = n;
+  if (flops) *flops = fl;
+  if (bytes) *bytes = by;
+  return QUIP_OK;
+}
 
 extern "C" int quip_qlinear_workspace_bytes(const QuipLinearDesc* d, int64_t M, size_t* out) {
   if (int e = check_desc(d)) return e;

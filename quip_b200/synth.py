@@ -52,3 +52,102 @@ def synth_layer_parts(K, N, bits=2, incoh='blocked', rescale=True, bias=False, s
         U = synth_butterfly(N, incoh, seed * 2 + 1, device)
         V = synth_butterfly(K, incoh, seed * 2 + 2, device)
     return LayerParts(bits=bits, qfn=qfn, codes=codes, scales=scales, zeros=zeros, bias=b, scaleWH=sWH, U=U, V=V)
+
+
+# ------------------------------------------------------------------------------------------------
+# whole synthetic models, built directly on the target device (nothing dense is ever materialised)
+# ------------------------------------------------------------------------------------------------
+def init_synthetic_(ql, seed=0, w_std=0.02):
+    """Fill a QuantLinear's buffers in place, on its own device, with a synthetic quantized layer:
+    uniform random packed words, the symmetric qfn 'b' grid, Haar-random butterfly factors, random
+    gather indices; 1/scaleWH is treated as already folded into the first V pass (as pack_parts does for
+    the as-run blocked butterfly)."""
+    dev = ql.qweight.device
+    gen = torch.Generator(device=dev).manual_seed(seed)
+    maxq = 2 ** ql.bits - 1
+    n_words = ql.qweight.numel()
+    ql.qweight.copy_(torch.randint(-2 ** 31, 2 ** 31 - 1, (n_words,), generator=gen, device=dev, dtype=torch.int64)
+                     .to(torch.int32))
+    s = float(torch.tensor(2.4 * w_std).half())
+    ql.scales.fill_(2 * s / maxq)
+    ql.zeros.fill_(s)
+    ql.meta[1] = 1
+    if ql.bias is not None:
+        ql.bias.copy_((0.02 * torch.randn(ql.outfeatures, generator=gen, device=dev)).half())
+    if ql.incoh:
+        for side, n in (('v', ql.infeatures), ('u', ql.outfeatures)):
+            idx = torch.arange(n, device=dev) if ql.incoh == 'noperm' else torch.randperm(n, generator=gen, device=dev)
+            getattr(ql, f'{side}_idx').copy_(idx.to(torch.int32))
+            ql.meta[3 if side == 'v' else 4] = int(ql.incoh == 'noperm')
+            for i in range(2):
+                buf = getattr(ql, f'{side}_f{i}')
+                nb, p, _ = buf.shape
+                for lo in range(0, nb, 256):
+                    hi = min(nb, lo + 256)
+                    buf[lo:hi].copy_(_haar(hi - lo, p, gen, dev).half())
+    if ql.rescale:
+        ql.inv_scale.fill_(1.0)
+        ql.meta[2] = 1 if ql.incoh in ('blocked', 'noperm') else 0
+    ql._desc = None
+    return ql
+
+
+def build_synthetic_model(config, device, bits=2, incoh='blocked', rescale=True, seed=0, seqlen=2048, dtype=torch.float16):
+    """A random-init HF OPT / Llama model whose decoder Linears are synthetic packed QuantLinears, created on
+    `device` without ever allocating the dense decoder weights (meta-device construction)."""
+    import torch.nn as nn
+    from .modelutils import find_layers
+    from .quant import QuantLinear
+    from transformers import LlamaConfig
+    is_llama = isinstance(config, LlamaConfig)
+    prev = torch.get_default_dtype()
+    torch.set_default_dtype(dtype)
+    try:
+        with torch.device('meta'):
+            if is_llama:
+                from transformers import LlamaForCausalLM
+                model = LlamaForCausalLM(config)
+            else:
+                from transformers import OPTForCausalLM
+                model = OPTForCausalLM(config)
+    finally:
+        torch.set_default_dtype(prev)
+    layers = model.model.layers if is_llama else model.model.decoder.layers
+    k = 0
+    for layer in layers:
+        for name, lin in find_layers(layer).items():
+            ql = QuantLinear(bits, lin.in_features, lin.out_features, bias=lin.bias is not None, incoh=incoh,
+                             rescale=rescale).to(device)
+            init_synthetic_(ql, seed=seed * 100003 + k)
+            k += 1
+            parent = layer
+            *path, leaf = name.split('.')
+            for part in path:
+                parent = getattr(parent, part)
+            setattr(parent, leaf, ql)
+    gen = torch.Generator(device=device).manual_seed(seed + 7)
+    for mod in model.modules():
+        for pname, p in list(mod._parameters.items()):
+            if p is None or not p.is_meta:
+                continue
+            t = torch.empty(p.shape, dtype=dtype, device=device)
+            if p.dim() == 1:
+                t.fill_(0.0 if pname == 'bias' else 1.0)          # norm weights 1, biases 0
+            else:
+                t.normal_(0.0, 0.02, generator=gen)
+            mod._parameters[pname] = nn.Parameter(t, requires_grad=False)
+        for bname, b in list(mod._buffers.items()):
+            if b is not None and b.is_meta:
+                mod._buffers[bname] = torch.zeros(b.shape, dtype=b.dtype, device=device)
+    if is_llama and hasattr(model.model, 'rotary_emb'):
+        model.model.rotary_emb = type(model.model.rotary_emb)(config=config, device=device)
+    model.seqlen = seqlen if is_llama else config.max_position_embeddings
+    return model.eval()
+
+
+LLAMA2_7B = dict(vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                 num_attention_heads=32, num_key_value_heads=32, max_position_embeddings=4096, rms_norm_eps=1e-5)
+OPT_1_3B = dict(vocab_size=50272, hidden_size=2048, ffn_dim=8192, num_hidden_layers=24, num_attention_heads=32,
+                max_position_embeddings=2048, word_embed_proj_dim=2048, do_layer_norm_before=True)
+OPT_125M = dict(vocab_size=50272, hidden_size=768, ffn_dim=3072, num_hidden_layers=12, num_attention_heads=12,
+                max_position_embeddings=2048, word_embed_proj_dim=768, do_layer_norm_before=True)

@@ -1,0 +1,169 @@
+"""Kernel-level timings at Llama-2-7B layer shapes (CUDA events, warm-up, rotating weight copies so the
+packed loads come from HBM).  Writes gpurun_out/microbench.json.  Not the bench contract (bench.py is)."""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from quip_b200 import _lib, quant as Q          # noqa: E402
+from quip_b200.synth import synth_layer_parts   # noqa: E402
+
+DEV = 'cuda:0'
+
+
+ITERS = None
+
+
+def timeit(fn, iters=50, warm=5):
+    if ITERS:
+        iters, warm = ITERS, 2
+    for _ in range(warm):
+        fn(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        fn(i)
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e3      # microseconds
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def bench_qgemm(N, K, M, bits, path, copies, peaks):
+    lib = _lib.load()
+    words = Q.packed_words(N, K, bits)
+    qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (copies, words), dtype=torch.int32, device=DEV)
+    sc = torch.full((N,), 0.01, device=DEV)
+    ze = sc * ((2 ** bits - 1) / 2)
+    x = torch.randn(M, K, device=DEV).half()
+    z = torch.empty(M, N, dtype=torch.float16, device=DEV)
+    descs = []
+    for c in range(copies):
+        d = _lib.QuipLinearDesc()
+        d.K, d.N, d.bits, d.flags = K, N, bits, _lib.QUIP_FLAG_SYMMETRIC
+        d.qweight, d.scales, d.zeros = qw[c].data_ptr(), sc.data_ptr(), ze.data_ptr()
+        descs.append(d)
+    need = C.c_size_t()
+    _lib.check(lib.quip_qlinear_workspace_bytes(C.byref(descs[0]), M, C.byref(need)))
+    ws = torch.zeros(need.value, dtype=torch.uint8, device=DEV)
+
+    def fn(i):
+        _lib.check(lib.quip_qgemm(C.byref(descs[i % copies]), _lib.ptr(x), None, None, _lib.ptr(z), M, path,
+                                  _lib.ptr(ws), ws.numel(), stream()))
+    us = timeit(fn)
+    code_bytes = N * K * bits / 8
+    alg_bytes = code_bytes + 2 * M * K + 2 * M * N
+    flops = 2.0 * M * N * K
+    return dict(kind='qgemm', N=N, K=K, M=M, bits=bits, path=path, us=us, GBps_codes_plus_act=alg_bytes / us / 1e3,
+                hbm_frac=alg_bytes / us / 1e3 / peaks['hbm_gbs'], TFLOPs=flops / us / 1e6,
+                tensor_frac=flops / us / 1e6 / peaks['bf16_tflops'])
+
+
+def bench_dense(N, K, M, peaks):
+    w = torch.randn(N, K, device=DEV).half()
+    x = torch.randn(M, K, device=DEV).half()
+    us = timeit(lambda i: torch.nn.functional.linear(x, w))
+    flops = 2.0 * M * N * K
+    return dict(kind='cublas_fp16_dense', N=N, K=K, M=M, us=us, TFLOPs=flops / us / 1e6,
+                GBps=(2 * N * K + 2 * M * K + 2 * M * N) / us / 1e3)
+
+
+def bench_layer(N, K, M, bits, incoh, peaks, copies=1):
+    mods = []
+    for c in range(copies):
+        tp = synth_layer_parts(K=K, N=N, bits=bits, incoh=incoh, rescale=incoh is not None, seed=c, device=DEV)
+        ql = Q.QuantLinear(infeatures=K, outfeatures=N, **Q.spec_from_parts(tp)).to(DEV)
+        ql.pack_parts(tp)
+        mods.append(ql)
+    x = torch.randn(M, K, device=DEV).half()
+    us = timeit(lambda i: mods[i % copies](x), iters=30)
+    flops = 2.0 * M * N * K
+    return dict(kind='qlinear_forward', N=N, K=K, M=M, bits=bits, incoh=incoh, us=us, TFLOPs_main=flops / us / 1e6)
+
+
+def bench_pass(n, p, nblk, strided, M):
+    lib = _lib.load()
+    f = (torch.randn(nblk, p, p, device=DEV) / p ** 0.5).half()
+    x = torch.randn(M, n, device=DEV).half()
+    out = torch.empty_like(x)
+    ps = _lib.QuipPass(p=p, nblk=nblk, strided=int(strided), shared=0, factors=f.data_ptr())
+
+    def fn(i):
+        _lib.check(lib.quip_rot_pass(C.byref(ps), _lib.ptr(x), _lib.ptr(out), M, n, 0, stream()))
+    us = timeit(fn, iters=30)
+    return dict(kind='rot_pass', n=n, p=p, nblk=nblk, strided=strided, M=M, us=us,
+                GBps=(4.0 * M * n + 2.0 * nblk * p * p) / us / 1e3, TFLOPs=2.0 * M * n * p / us / 1e6)
+
+
+def bench_gather(n, M):
+    lib = _lib.load()
+    x = torch.randn(M, n, device=DEV).half()
+    out = torch.empty_like(x)
+    idx = torch.randperm(n, device=DEV).int()
+    us = timeit(lambda i: _lib.check(lib.quip_gather(_lib.ptr(x), _lib.ptr(out), M, n, _lib.ptr(idx), None, None, stream())), iters=30)
+    return dict(kind='gather', n=n, M=M, us=us, GBps=4.0 * M * n / us / 1e3)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--what', default='qgemm,dense,pass,layer')
+    ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'microbench.json'))
+    ap.add_argument('--iters', type=int, default=0)
+    a = ap.parse_args()
+    global ITERS
+    ITERS = a.iters or None
+    peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(
+        os.path.join(ROOT, 'MEASURED_PEAKS.json')) else dict(hbm_gbs=6650.0, bf16_tflops=1590.0)
+    res = []
+    what = a.what.split(',')
+    shapes = [(4096, 4096), (11008, 4096), (4096, 11008)]
+    if 'qgemm' in what:
+        for (N, K) in shapes:
+            copies = max(2, int(300e6 // (N * K // 4)))
+            for M in (1, 8, 16, 32):
+                res.append(bench_qgemm(N, K, M, 2, 1, copies, peaks)); print(res[-1], flush=True)
+            for M in (64, 128, 256, 2048):
+                res.append(bench_qgemm(N, K, M, 2, 2, 2, peaks)); print(res[-1], flush=True)
+        for bits in (3, 4):
+            res.append(bench_qgemm(4096, 4096, 1, bits, 1, 20, peaks)); print(res[-1], flush=True)
+            res.append(bench_qgemm(4096, 4096, 2048, bits, 2, 2, peaks)); print(res[-1], flush=True)
+        # a stacked matrix (32 x 11008 rows): the skinny kernel's steady-state bandwidth, launch ramp amortised
+        res.append(bench_qgemm(32 * 11008, 4096, 1, 2, 1, 2, peaks)); print(res[-1], flush=True)
+        res.append(bench_qgemm(32 * 11008, 4096, 16, 2, 1, 2, peaks)); print(res[-1], flush=True)
+    if 'prof_tc' in what:
+        res.append(bench_qgemm(4096, 4096, 2048, 2, 2, 2, peaks)); print(res[-1], flush=True)
+        res.append(bench_qgemm(11008, 4096, 2048, 2, 2, 2, peaks)); print(res[-1], flush=True)
+    if 'prof_skinny' in what:
+        res.append(bench_qgemm(11008, 4096, 1, 2, 1, 8, peaks)); print(res[-1], flush=True)
+        res.append(bench_qgemm(32 * 11008, 4096, 1, 2, 1, 2, peaks)); print(res[-1], flush=True)
+    if 'dense' in what:
+        for (N, K) in shapes:
+            for M in (1, 2048):
+                res.append(bench_dense(N, K, M, peaks)); print(res[-1], flush=True)
+    if 'pass' in what:
+        for M in (1, 2048):
+            for (n, p, nblk, st) in [(4096, 64, 64, False), (4096, 64, 64, True), (11008, 688, 16, False), (11008, 16, 688, True)]:
+                res.append(bench_pass(n, p, nblk, st, M)); print(res[-1], flush=True)
+            res.append(bench_gather(4096, M)); print(res[-1], flush=True)
+            res.append(bench_gather(11008, M)); print(res[-1], flush=True)
+    if 'layer' in what:
+        for (N, K) in shapes:
+            for M in (1, 2048):
+                res.append(bench_layer(N, K, M, 2, 'blocked', peaks)); print(res[-1], flush=True)
+        res.append(bench_layer(4096, 4096, 2048, 2, None, peaks)); print(res[-1], flush=True)
+        res.append(bench_layer(4096, 4096, 2048, 2, 'kron', peaks)); print(res[-1], flush=True)
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    json.dump(res, open(a.out, 'w'), indent=1)
+
+
+if __name__ == '__main__':
+    main()
