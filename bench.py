@@ -186,8 +186,11 @@ def main():
         lib.quip_timing_enable(1)
         launches0 = lib.quip_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        profiling = os.environ.get('QUIP_PROFILE') == '1'     # ncu --profile-from-start off: timed region only
         with ClockSampler(local) as clk:
             barrier()
+            if profiling:
+                torch.cuda.profiler.start()
             e0.record()
             nll = torch.zeros((), device=dev)
             for i in range(a.warmup, total):
@@ -196,6 +199,8 @@ def main():
                 dist.all_reduce(nll)
             e1.record()
             barrier()
+            if profiling:
+                torch.cuda.profiler.stop()
         ms = max_over_ranks(e0.elapsed_time(e1))
         launches = lib.quip_launch_count() - launches0
         lib.quip_timing_enable(0)

@@ -44,6 +44,7 @@ EXPORTS = {
     'quip_unpack_codes': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'quip_convert_ref': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'quip_packed_words': (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    'quip_config': (C.c_int, [C.c_char_p, C.c_int]),
     'quip_timing_enable': (C.c_int, [C.c_int]),
     'quip_timing_reset': (C.c_int, []),
     'quip_timing_read': (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_double),

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, 'build')
 LIB = os.path.join(HERE, 'libquip_b200.so')
-SOURCES = ['api.cu', 'pack.cu', 'rot.cu', 'qgemm_skinny.cu', 'qgemm_tc.cu']
+SOURCES = ['api.cu', 'pack.cu', 'rot.cu', 'rot_small.cu', 'qgemm_skinny.cu', 'qgemm_tc.cu', 'qgemm_tc2.cu']
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '--expt-relaxed-constexpr']
@@ -29,7 +29,7 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(OBJ, exist_ok=True)
-    headers = [os.path.join(CSRC, 'common.cuh'), os.path.join(os.path.dirname(HERE), 'include', 'quip_b200.h')]
+    headers = [os.path.join(CSRC, 'common.cuh'), os.path.join(CSRC, 'tc_common.cuh'), os.path.join(os.path.dirname(HERE), 'include', 'quip_b200.h')]
     jobs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)

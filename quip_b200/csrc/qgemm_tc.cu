@@ -15,135 +15,9 @@
 //   warps 6-9   weight producers: 128-bit loads of packed words -> registers -> fp16 -> smem
 // Pipelines: smem ring full[s]/empty[s] (TMA + 4 producer warps -> MMA -> tcgen05.commit), and a
 // double-buffered TMEM accumulator tmem_full[a]/tmem_empty[a] (MMA -> epilogue).
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace quip {
-
-constexpr int TC_BM = 128;            // output rows per tile (MMA M)
-constexpr int TC_BK = 64;             // k per stage = one 128-byte swizzle atom of fp16
-constexpr int TC_THREADS = 320;
-constexpr uint32_t TC_WATCHDOG = 1u << 28;
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar), done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > TC_WATCHDOG) __trap();      // a protocol bug must not hang the GPU
-  }
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16, single CTA
-__device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);        // start address, bits [0,14)
-  d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                    // stride byte offset: 8 rows * 128 B
-  d |= (uint64_t)1 << 46;                              // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
-  return d;
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// packed words one producer thread needs for one (row block, lane) over one k super-block (128 k)
-template <int BITS>
-struct TcWords {
-  uint32_t w[BITS == 2 ? 4 : (BITS == 3 ? 6 : 8)];
-};
-template <int BITS>
-__device__ __forceinline__ void tc_load_words(const uint32_t* __restrict__ sb, int l, TcWords<BITS>& r, bool valid) {
-  if (!valid) {
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(r.w) / 4); ++i) r.w[i] = 0;
-    return;
-  }
-  if constexpr (BITS == 2) {
-    uint4 v = *reinterpret_cast<const uint4*>(sb + l * 4);
-    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
-  } else if constexpr (BITS == 4) {
-    uint4 a = *reinterpret_cast<const uint4*>(sb + l * 4), b = *reinterpret_cast<const uint4*>(sb + 128 + l * 4);
-    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
-    r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
-  } else {
-    uint4 a = *reinterpret_cast<const uint4*>(sb + l * 4);
-    uint2 b = *reinterpret_cast<const uint2*>(sb + 128 + l * 2);
-    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
-    r.w[4] = b.x; r.w[5] = b.y;
-  }
-}
-// expand chunk CH (0..3) of a super-block and store rows g / g+8 of row block `rbl` into the stage's A tile
-template <int BITS, int CH>
-__device__ __forceinline__ void tc_store_chunk(const TcWords<BITS>& r, uint32_t a_tile, int rbl, int g, int t,
-                                               bool valid) {
-  uint32_t h[8];
-  if (valid) {
-    if constexpr (BITS == 2) expand_chunk<2>(r.w[CH], 0u, h);
-    else if constexpr (BITS == 4) expand_chunk<4>(r.w[2 * CH], r.w[2 * CH + 1], h);
-    else expand_chunk<3, (CH & 1)>(r.w[CH], r.w[4 + (CH >> 1)], h);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) h[i] = 0;     // rows beyond N contribute exact zeros
-  }
-  const int cidx = (CH & 1) * 4 + t;          // 16-byte chunk inside the 128-byte row of this stage
-  const uint32_t off = (uint32_t)(rbl * 16 + g) * 128u + (uint32_t)((cidx ^ g) << 4);
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a_tile + off), "r"(h[0]), "r"(h[2]), "r"(h[4]), "r"(h[6])
-               : "memory");
-  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a_tile + off + 8u * 128u), "r"(h[1]), "r"(h[3]),
-               "r"(h[5]), "r"(h[7])
-               : "memory");
-}
 
 template <int BN>
 struct TcCfg {
@@ -155,11 +29,16 @@ struct TcCfg {
   static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BITS, int BN>
+// DENSE = false: A is the packed matrix (N rows, K columns), expanded by the producer warps.
+// DENSE = true : block-diagonal pass with big blocks -- `nblk` independent GEMMs out_b = in_b . F_b^T, A = fp16
+//                factor F_b (N = K = p) fetched by TMA (3-D map, rows/cols beyond p zero-filled), B = the
+//                block's p contiguous activation columns, output written to the same columns.
+template <int BITS, int BN, bool DENSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __restrict__ q,
-                const float* __restrict__ scales, const float* __restrict__ zeros, const __half* __restrict__ bias,
-                const float* __restrict__ xsum, __half* __restrict__ z, int M, int K, int N, int symmetric) {
+qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_a,
+                const uint32_t* __restrict__ q, const float* __restrict__ scales, const float* __restrict__ zeros,
+                const __half* __restrict__ bias, const float* __restrict__ xsum, __half* __restrict__ z, int M, int K,
+                int N, int symmetric, int nblk, int shared_factor) {
   using C = TcCfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -174,14 +53,17 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __re
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (N + TC_BM - 1) / TC_BM;
   const int tiles_m = (M + BN - 1) / BN;
-  const int num_tiles = tiles_n * tiles_m;
-  const int KB = K / TC_BK;
+  const int per_blk = tiles_n * tiles_m;
+  const int num_tiles = per_blk * nblk;
+  const int KB = (K + TC_BK - 1) / TC_BK;
   const int KSB = K >> 7;
+  const int64_t ldz = (int64_t)N * nblk;       // output row pitch (== N for the packed GEMM)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+    if (DENSE) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_a) : "memory");
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(&full[s], 1 + 4);              // TMA producer + 4 weight-producer warps
+      mbar_init(&full[s], DENSE ? 1 : 1 + 4);  // TMA producer (+ 4 weight-producer warps)
       mbar_init(&empty[s], 1);                 // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -207,11 +89,14 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __re
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BN;
+        const int blk = tile / per_blk, rr = tile % per_blk;
+        const int m0 = (rr / tiles_n) * BN, n0 = (rr % tiles_n) * TC_BM;
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full[s], C::B_BYTES);
-          tma_load_2d(smem_gen + (size_t)s * C::STAGE_BYTES + C::A_BYTES, &tmap_x, &full[s], kb * TC_BK, m0);
+          mbar_arrive_expect_tx(&full[s], DENSE ? C::STAGE_BYTES : C::B_BYTES);
+          unsigned char* stage = smem_gen + (size_t)s * C::STAGE_BYTES;
+          if (DENSE) tma_load_3d(stage, &tmap_a, &full[s], kb * TC_BK, n0, shared_factor ? 0 : blk);
+          tma_load_2d(stage + C::A_BYTES, &tmap_x, &full[s], blk * K + kb * TC_BK, m0);
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -252,15 +137,17 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __re
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-      const int n = (tile % tiles_n) * TC_BM + quarter * 32 + lane;
-      const int m0 = (tile / tiles_n) * BN;
-      float Pn = 0.f, Rn = 0.f, bn = 0.f;
-      if (n < N) {
+      const int blk = tile / per_blk, rr = tile % per_blk;
+      const int n = (rr % tiles_n) * TC_BM + quarter * 32 + lane;
+      const int m0 = (rr / tiles_n) * BN;
+      float Pn = 1.f, Rn = 0.f, bn = 0.f;
+      if (!DENSE && n < N) {
         float sc = scales[n];
         Pn = sc * (float)(1 << BITS);
         if (!symmetric) Rn = sc * (0.5f * (float)((1 << BITS) - 1)) - zeros[n];
         if (bias) bn = __half2float(bias[n]);
       }
+      __half* zcol = z + (int64_t)blk * N + n;
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
@@ -275,8 +162,8 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __re
             const int m = m0 + c0 + c;
             if (m < M) {
               float v = Pn * __uint_as_float(r[c]) + bn;
-              if (!symmetric) v += Rn * __ldg(&xsum[m]);
-              z[(int64_t)m * N + n] = __float2half_rn(v);
+              if (!DENSE && !symmetric) v += Rn * __ldg(&xsum[m]);
+              zcol[(int64_t)m * ldz] = __float2half_rn(v);
             }
           }
         }
@@ -285,7 +172,7 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __re
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
     }
-  } else {
+  } else if (!DENSE) {
     // ================= weight producers: packed words -> fp16 operand tile =================
     const int pw = warp - 6;                       // 0..3
     const int g = lane & 7, t = lane >> 3;         // 8 consecutive lanes = 8 rows g: conflict-free st.shared.v4
@@ -293,7 +180,7 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __re
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int rb_base = (tile % tiles_n) * (TC_BM / 16);
+      const int rb_base = ((tile % per_blk) % tiles_n) * (TC_BM / 16);
       const int NRB = N >> 4;
       // this thread serves row blocks pw and pw+4 of the tile
       const int rbl0 = pw, rbl1 = pw + 4;
@@ -361,40 +248,87 @@ static PFN_encodeTiled get_encode() {
 
 static int g_num_sms = 0;
 
-template <int BITS, int BN>
-static int launch_tc(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z,
-                     int M, cudaStream_t s) {
-  using C = TcCfg<BN>;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// activations (rows, cols) fp16 row-major -> 2-D map, box {64 cols, box_rows}, 128B swizzle, zero OOB fill
+int make_act_map(CUtensorMap* tmap, const void* x, int64_t rows, int64_t cols, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return QUIP_ERR_CUDA;
   }
-  CUtensorMap tmap;
-  cuuint64_t dims[2] = {(cuuint64_t)d->K, (cuuint64_t)M};
-  cuuint64_t strides[1] = {(cuuint64_t)d->K * sizeof(__half)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__half)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)x, dims, strides, box, estr,
+  CUresult r = enc(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, (void*)x, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed with CUresult %d (x=%p M=%d K=%d)", (int)r, (const void*)x, M, d->K);
+    set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr=%p rows=%lld cols=%lld)", (int)r, x,
+              (long long)rows, (long long)cols);
     return QUIP_ERR_CUDA;
   }
-  if (!g_num_sms) {
-    int dev = 0;
-    QUIP_CUDA(cudaGetDevice(&dev));
-    QUIP_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
-  auto kern = qgemm_tc_kernel<BITS, BN>;
+  return QUIP_OK;
+}
+
+template <int BITS, int BN>
+static int launch_tc(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z,
+                     int M, cudaStream_t s) {
+  using C = TcCfg<BN>;
+  CUtensorMap tmap;
+  if (int e = make_act_map(&tmap, x, M, d->K, BN)) return e;
+  auto kern = qgemm_tc_kernel<BITS, BN, false>;
   QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
   int tiles = ceil_div(d->N, TC_BM) * ceil_div(M, BN);
-  int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  kern<<<grid, TC_THREADS, C::SMEM, s>>>(tmap, reinterpret_cast<const uint32_t*>(d->qweight), d->scales, d->zeros, bias,
-                                         xsum, z, M, d->K, d->N, (d->flags & QUIP_FLAG_SYMMETRIC) ? 1 : 0);
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, TC_THREADS, C::SMEM, s>>>(tmap, tmap, reinterpret_cast<const uint32_t*>(d->qweight), d->scales, d->zeros,
+                                         bias, xsum, z, M, d->K, d->N, (d->flags & QUIP_FLAG_SYMMETRIC) ? 1 : 0, 1, 0);
   QUIP_LAUNCHED("qgemm_tc_kernel");
   return QUIP_OK;
+}
+
+// block-diagonal pass with big contiguous blocks on the tensor cores (see DENSE in the kernel)
+template <int BN>
+static int launch_tc_dense(const QuipPass* ps, const __half* in, __half* out, int M, int n, cudaStream_t s) {
+  using C = TcCfg<BN>;
+  PFN_encodeTiled enc = get_encode();
+  CUtensorMap tmx, tma;
+  if (int e = make_act_map(&tmx, in, M, n, BN)) return e;
+  const int p = ps->p;
+  cuuint64_t dims[3] = {(cuuint64_t)p, (cuuint64_t)p, (cuuint64_t)(ps->shared ? 1 : ps->nblk)};
+  cuuint64_t strides[2] = {(cuuint64_t)p * sizeof(__half), (cuuint64_t)p * p * sizeof(__half)};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(&tma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ps->factors, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (factors) failed with CUresult %d (p=%d nblk=%d)", (int)r, p, ps->nblk);
+    return QUIP_ERR_CUDA;
+  }
+  auto kern = qgemm_tc_kernel<2, BN, true>;
+  QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
+  int tiles = ceil_div(p, TC_BM) * ceil_div(M, BN) * ps->nblk;
+  int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, TC_THREADS, C::SMEM, s>>>(tmx, tma, nullptr, nullptr, nullptr, nullptr, nullptr, out, M, p, p, 1,
+                                         ps->nblk, ps->shared ? 1 : 0);
+  QUIP_LAUNCHED("qgemm_tc_kernel<dense>");
+  return QUIP_OK;
+}
+
+int pass_big_tc(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s) {
+  QUIP_CHECK_ARG(!ps->strided && ps->p % 8 == 0 && n % 8 == 0, "tcgen05 pass needs contiguous blocks, p %% 8 == 0");
+  QUIP_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ps->factors) & 15) == 0, "tcgen05 pass: unaligned pointer");
+  return M > 128 ? launch_tc_dense<256>(ps, in, out, (int)M, n, s) : launch_tc_dense<128>(ps, in, out, (int)M, n, s);
 }
 
 int qgemm_tc(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,

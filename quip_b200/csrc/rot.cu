@@ -18,30 +18,43 @@
 namespace quip {
 
 // ----------------------------------------------------------------------------------------------
+// R rows per CTA share one read of the index vector (4 bytes/feature, twice the fp16 row itself)
+template <int R>
 __global__ void __launch_bounds__(256) gather_kernel(const __half* __restrict__ in, __half* __restrict__ out,
-                                                     int n, const int32_t* __restrict__ idx,
+                                                     int64_t M, int n, const int32_t* __restrict__ idx,
                                                      const float* __restrict__ scale,
                                                      const __half* __restrict__ bias) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __half* row = reinterpret_cast<__half*>(smem_raw);
-  const int64_t m = blockIdx.x;
-  const __half* src = in + m * n;
-  for (int c = threadIdx.x; c < n / 8; c += blockDim.x)
-    reinterpret_cast<uint4*>(row)[c] = reinterpret_cast<const uint4*>(src)[c];
+  __half* rows = reinterpret_cast<__half*>(smem_raw);            // [R][n]
+  const int64_t m0 = (int64_t)blockIdx.x * R;
+  const int nr = (int)((M - m0) < R ? (M - m0) : R);
+  const int cpr = n / 8;
+  for (int c = threadIdx.x; c < nr * cpr; c += blockDim.x)
+    reinterpret_cast<uint4*>(rows)[c] = ldg_nc_v4(in + m0 * n + (int64_t)c * 8);
   __syncthreads();
-  __half* dst = out + m * n;
-  for (int c = threadIdx.x; c < n / 8; c += blockDim.x) {
-    int l0 = c * 8;
-    __align__(16) __half v[8];
+  for (int c = threadIdx.x; c < cpr; c += blockDim.x) {
+    const int l0 = c * 8;
+    int src[8];
+    float sc[8], bs[8];
+    if (idx) {
+      const int4 a = *reinterpret_cast<const int4*>(idx + l0), b = *reinterpret_cast<const int4*>(idx + l0 + 4);
+      src[0] = a.x; src[1] = a.y; src[2] = a.z; src[3] = a.w; src[4] = b.x; src[5] = b.y; src[6] = b.z; src[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) src[i] = l0 + i;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      int s = idx ? idx[l0 + i] : (l0 + i);
-      float f = __half2float(row[s]);
-      if (scale) f *= scale[s];
-      if (bias) f += __half2float(bias[l0 + i]);
-      v[i] = __float2half_rn(f);
+      sc[i] = scale ? scale[src[i]] : 1.f;
+      bs[i] = bias ? __half2float(bias[l0 + i]) : 0.f;
     }
-    reinterpret_cast<uint4*>(dst)[c] = *reinterpret_cast<uint4*>(v);
+    for (int r = 0; r < nr; ++r) {
+      __align__(16) __half v[8];
+      const __half* row = rows + (size_t)r * n;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = __float2half_rn(fmaf(__half2float(row[src[i]]), sc[i], bs[i]));
+      *reinterpret_cast<uint4*>(out + (m0 + r) * n + l0) = *reinterpret_cast<const uint4*>(v);
+    }
   }
 }
 
@@ -369,18 +382,32 @@ pass_big_kernel(const __half* __restrict__ in, __half* __restrict__ out, const _
 
 using namespace quip;
 
+template <int R>
+static int launch_gather(const __half* in, __half* out, int64_t M, int n, const int32_t* idx, const float* scale,
+                         const __half* bias, cudaStream_t s) {
+  size_t smem = (size_t)R * n * sizeof(__half);
+  auto kern = gather_kernel<R>;
+  if (smem > 48 * 1024) QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<ceil_div(M, R), 256, smem, s>>>(in, out, M, n, idx, scale, bias);
+  QUIP_LAUNCHED("gather_kernel");
+  return QUIP_OK;
+}
+
 extern "C" int quip_gather(const void* in, void* out, int64_t M, int32_t n, const int32_t* idx,
                            const float* scale, const void* bias, void* stream) {
   QUIP_CHECK_ARG(in && out && M > 0 && n > 0 && n % 8 == 0, "gather: bad arguments (M=%lld n=%d)", (long long)M, n);
   QUIP_CHECK_ARG(in != out, "gather cannot run in place");
-  size_t smem = (size_t)n * sizeof(__half);
-  QUIP_CHECK_ARG(smem <= 200 * 1024, "gather: n=%d too large", n);
-  if (smem > 48 * 1024)
-    QUIP_CUDA(cudaFuncSetAttribute(gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  gather_kernel<<<(unsigned)M, 256, smem, (cudaStream_t)stream>>>((const __half*)in, (__half*)out, n, idx, scale,
-                                                                 (const __half*)bias);
-  QUIP_LAUNCHED("gather_kernel");
-  return QUIP_OK;
+  QUIP_CHECK_ARG((size_t)n * sizeof(__half) <= 200 * 1024, "gather: n=%d too large", n);
+  cudaStream_t s = (cudaStream_t)stream;
+  const __half* i = (const __half*)in;
+  __half* o = (__half*)out;
+  const __half* b = (const __half*)bias;
+  // rows per CTA: as many as fit ~96 KB of shared memory (2 CTAs / SM), fewer when M is small
+  const size_t row = (size_t)n * sizeof(__half);
+  if (M >= 8 * 148 && 8 * row <= 96 * 1024) return launch_gather<8>(i, o, M, n, idx, scale, b, s);
+  if (M >= 4 * 148 && 4 * row <= 96 * 1024) return launch_gather<4>(i, o, M, n, idx, scale, b, s);
+  if (M >= 2 * 148 && 2 * row <= 96 * 1024) return launch_gather<2>(i, o, M, n, idx, scale, b, s);
+  return launch_gather<1>(i, o, M, n, idx, scale, b, s);
 }
 
 extern "C" int quip_rowsum(const void* x, float* xsum, int64_t M, int32_t K, void* stream) {
@@ -388,6 +415,11 @@ extern "C" int quip_rowsum(const void* x, float* xsum, int64_t M, int32_t K, voi
   rowsum_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>((const __half*)x, xsum, M, K);
   QUIP_LAUNCHED("rowsum_kernel");
   return QUIP_OK;
+}
+
+namespace quip {
+int pass_big_tc(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s);
+int launch_small_fast(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s, bool* handled);
 }
 
 template <int P>
@@ -418,11 +450,16 @@ extern "C" int quip_rot_pass(const QuipPass* ps, const void* in_, void* out_, in
   bool small_ok = p <= 64;
   bool big_ok = p > 64 && !ps->strided && p % 8 == 0 && n % 8 == 0;
   if (impl != 1 && small_ok) {
+    bool handled = false;
+    if (int e = launch_small_fast(ps, in, out, M, n, s, &handled)) return e;
+    if (handled) return QUIP_OK;
     if (p <= 16) return launch_small<16>(ps, in, out, M, n, s);
     if (p <= 32) return launch_small<32>(ps, in, out, M, n, s);
     if (p <= 48) return launch_small<48>(ps, in, out, M, n, s);
     return launch_small<64>(ps, in, out, M, n, s);
   }
+  if (impl != 1 && impl != 3 && big_ok && M > 32 && ((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ps->factors) & 15) == 0))
+    return pass_big_tc(ps, in, out, M, n, s);      // tcgen05: the 688x688 blocks of an 11008 side are real GEMMs
   if (impl != 1 && big_ok) {
     size_t smem = (size_t)BIG_STAGES * (BIG_BM + BIG_BN) * BIG_LD * sizeof(__half);
     QUIP_CUDA(cudaFuncSetAttribute(pass_big_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

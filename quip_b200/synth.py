@@ -13,10 +13,26 @@ from .capture import Butterfly, LayerParts, butterfly_factors
 
 
 def _haar(m, p, gen, device):
+    """m Haar-random p x p orthogonal matrices (QR of a Gaussian, sign-fixed) -- what scipy's
+    special_ortho_group gives the reference (method.py:22)."""
     a = torch.randn(m, p, p, generator=gen, device=device)
     q, r = torch.linalg.qr(a)
     d = torch.diagonal(r, dim1=-2, dim2=-1)
     return q * torch.sign(d).unsqueeze(-2)
+
+
+def _fast_ortho(m, p, gen, device):
+    """m dense random orthogonal p x p matrices as a product of two Householder reflections: exactly
+    orthogonal, fully dense, and ~100x cheaper to generate than a batched QR (used to build whole synthetic
+    models; the kernels' cost does not depend on which orthogonal matrix they multiply by)."""
+    eye = torch.eye(p, device=device).expand(m, p, p)
+    out = None
+    for _ in range(2):
+        v = torch.randn(m, p, 1, generator=gen, device=device)
+        v = v / v.norm(dim=1, keepdim=True)
+        h = eye - 2.0 * v @ v.transpose(1, 2)
+        out = h if out is None else out @ h
+    return out
 
 
 def synth_butterfly(n, mode='blocked', seed=0, device='cpu'):
@@ -84,7 +100,7 @@ def init_synthetic_(ql, seed=0, w_std=0.02):
                 nb, p, _ = buf.shape
                 for lo in range(0, nb, 256):
                     hi = min(nb, lo + 256)
-                    buf[lo:hi].copy_(_haar(hi - lo, p, gen, dev).half())
+                    buf[lo:hi].copy_(_fast_ortho(hi - lo, p, gen, dev).half())
     if ql.rescale:
         ql.inv_scale.fill_(1.0)
         ql.meta[2] = 1 if ql.incoh in ('blocked', 'noperm') else 0
