@@ -99,7 +99,19 @@ def cpu_reference_arm(steps, warmup):
     from oracle.evalloop import reference_eval
     from quip_b200.llama import get_llama
     from quip_b200.synth import LLAMA2_7B
-    cores = os.cpu_count() or 1
+    ncpu = os.cpu_count() or 1
+    # use the thread count at which the host's fp16 GEMM is fastest (more threads is not always faster)
+    probe_x, probe_w = torch.randn(SEQ, 4096).half(), torch.randn(4096, 4096).half()
+    best = (float('inf'), ncpu)
+    for nt in sorted({min(ncpu, c) for c in (8, 16, 32, 64, ncpu)}):
+        torch.set_num_threads(nt)
+        torch.nn.functional.linear(probe_x, probe_w)
+        t0 = time.perf_counter()
+        torch.nn.functional.linear(probe_x, probe_w)
+        dt = time.perf_counter() - t0
+        if dt < best[0]:
+            best = (dt, nt)
+    cores = best[1]
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     cfg = LlamaConfig(**{**LLAMA2_7B, 'num_hidden_layers': 1})
@@ -157,6 +169,8 @@ def main():
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     lib = _lib.load()
+    if os.environ.get('QUIP_TC2') == '1':
+        lib.quip_config(b'tc2', 1)
 
     cfg = LlamaConfig(**{**LLAMA2_7B, 'num_hidden_layers': a.layers})
     model = build_synthetic_model(cfg, dev, bits=2, incoh='blocked', rescale=True, seed=rank, seqlen=SEQ)
@@ -239,7 +253,8 @@ def main():
     out = dict(base, value=value, ms_per_step=ms / a.steps, dtype='f16', impl='ours', gpu_launches=int(launches),
                e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=SEQ * 8, d2h_bytes_per_step=4,
                         api='quip_b200.llama.llama_eval'),
-               roofline=dict(bound='tensor', kernel='qgemm_tc_kernel<2,256> (tcgen05 packed GEMM)', achieved=achieved,
+               roofline=dict(bound='tensor', kernel=('qgemm_tc2_kernel<2> (tcgen05 cta_group::2 packed GEMM)' if os.environ.get('QUIP_TC2') == '1'
+                                     else 'qgemm_tc_kernel<2,256> (tcgen05 packed GEMM)'), achieved=achieved,
                              peak=pk['tflops_sustained'], unit='TFLOP/s', frac=(achieved / pk['tflops_sustained']) if achieved else None,
                              traffic=traffic, launches_timed=int(tn.value), kernel_ms_per_step=tms.value / a.steps,
                              share_of_step=tms.value / ms, peak_source=pk['source'] + ', sustained bf16 (kernel timed inside a long step)'),

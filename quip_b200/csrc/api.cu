@@ -33,6 +33,8 @@ int qgemm_tc(const QuipLinearDesc* d, const __half* x, const float* xsum, const 
 int qgemm_tc2(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
               cudaStream_t s);
 
+extern int g_gather_rows, g_pass_min_tiles;   // rot.cu
+
 // tuning knobs (quip_config)
 static int g_use_tc2 = 0;        // route big-M contractions to the 2-CTA kernel
 
@@ -143,6 +145,8 @@ extern "C" int64_t quip_launch_count(void) { return g_launches.load(); }
 extern "C" int quip_config(const char* key, int value) {
   QUIP_CHECK_ARG(key != nullptr, "null key");
   if (!strcmp(key, "tc2")) { g_use_tc2 = value; return QUIP_OK; }
+  if (!strcmp(key, "gather_rows")) { g_gather_rows = value; return QUIP_OK; }
+  if (!strcmp(key, "pass_min_tiles")) { g_pass_min_tiles = value > 0 ? value : 1; return QUIP_OK; }
   set_error("quip_config: unknown key '%s'", key);
   return QUIP_ERR_ARG;
 }

@@ -68,7 +68,7 @@ qgemm_skinny_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x
   float* xsum_s = red + SK_WARPS * TOK * RLD;                                      // [TOK]
   __shared__ int s_last;
 
-  // ---- stage the activations of this K range: xs[tok][k] ----
+  // ---- stage the activations of this K range once per CTA: xs[tok][k] ----
   {
     const int cpr = kslice / 8;
     for (int c = tid; c < TOK * cpr; c += SK_WARPS * 32) {
@@ -89,109 +89,139 @@ qgemm_skinny_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x
     }
   }
 
-  const int rb0 = blockIdx.x * RBC;                       // first 16-row block of this CTA
   const int NRB = N >> 4;
-  float acc[RBC][NT8][4];
-#pragma unroll
-  for (int a = 0; a < RBC; ++a)
-#pragma unroll
-    for (int b = 0; b < NT8; ++b)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
-
-  for (int ksb = ksb0 + warp; ksb < ksb1; ksb += SK_WARPS) {
-    SbRegs<BITS> wr[RBC];
-#pragma unroll
-    for (int r = 0; r < RBC; ++r) {
-      int rb = min(rb0 + r, NRB - 1);                     // tail tile: re-read a valid block, masked at the store
-      load_sb<BITS>(q + ((int64_t)rb * KSB + ksb) * sb_words(BITS), lane, wr[r]);
-    }
-    const __half* xk = xs + (ksb - ksb0) * 128 + 8 * t;
-    auto do_chunk = [&](auto chc) {
-      constexpr int CH = decltype(chc)::value;
-      uint32_t xb[NT8][4];
-#pragma unroll
-      for (int nt = 0; nt < NT8; ++nt) {
-        uint4 v = *reinterpret_cast<const uint4*>(xk + (nt * 8 + g) * xld + CH * 32);
-        xb[nt][0] = v.x; xb[nt][1] = v.y; xb[nt][2] = v.z; xb[nt][3] = v.w;
-      }
-#pragma unroll
-      for (int r = 0; r < RBC; ++r) {
-        uint32_t h[8];
-        expand_sb_chunk<BITS, CH>(wr[r], h);
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          uint32_t a[4] = {h[4 * s], h[4 * s + 1], h[4 * s + 2], h[4 * s + 3]};
-#pragma unroll
-          for (int nt = 0; nt < NT8; ++nt) {
-            uint32_t b[2] = {xb[nt][2 * s], xb[nt][2 * s + 1]};
-            mma16816(acc[r][nt], a, b);
-          }
-        }
-      }
-    };
-    do_chunk(std::integral_constant<int, 0>{});
-    do_chunk(std::integral_constant<int, 1>{});
-    do_chunk(std::integral_constant<int, 2>{});
-    do_chunk(std::integral_constant<int, 3>{});
-  }
-
-  // ---- reduce the 8 warps: red[warp][tok][row] ----
-#pragma unroll
-  for (int r = 0; r < RBC; ++r)
-#pragma unroll
-    for (int nt = 0; nt < NT8; ++nt) {
-      float* b = red + (warp * TOK + nt * 8 + 2 * t) * RLD + r * 16 + g;
-      b[0] = acc[r][nt][0];
-      b[RLD] = acc[r][nt][1];
-      b[8] = acc[r][nt][2];
-      b[RLD + 8] = acc[r][nt][3];
-    }
-  __syncthreads();
-
-  const int n0 = rb0 * 16;
+  const int ntiles = (NRB + RBC - 1) / RBC;               // row tiles in the matrix
+  const int nk = ksb1 - ksb0;
+  const int rounds = (nk + SK_WARPS - 1) / SK_WARPS;      // k iterations per warp per row tile (lockstep)
   const int nsplit = gridDim.y;
   const bool direct = nsplit == 1;
-  for (int e = tid; e < TOK * ROWS; e += SK_WARPS * 32) {
-    int tok = e / ROWS, r = e % ROWS;
-    int n = n0 + r;
-    if (tok >= M || n >= N) continue;
-    float s = 0.f;
-#pragma unroll
-    for (int w = 0; w < SK_WARPS; ++w) s += red[(w * TOK + tok) * RLD + r];
-    float sc = scales[n];
-    float v = sc * (float)(1 << BITS) * s;
-    if (!symmetric) v += (sc * (0.5f * (float)((1 << BITS) - 1)) - zeros[n]) * xsum_s[tok];
-    if (direct) {
-      if (bias) v += __half2float(bias[n]);
-      z[(int64_t)tok * N + n] = __float2half_rn(v);
-    } else {
-      part[((int64_t)blockIdx.y * M + tok) * N + n] = v;
-    }
-  }
-  if (direct) return;
 
-  // ---- K splits: the last CTA of this row tile sums the partials in split order ----
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    int prev = atomicAdd(&counters[blockIdx.x], 1);
-    s_last = (prev == nsplit - 1);
-    if (s_last) counters[blockIdx.x] = 0;                 // leave the header zeroed for the next call
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int e = tid; e < TOK * ROWS; e += SK_WARPS * 32) {
-    int tok = e / ROWS, r = e % ROWS;
-    int n = n0 + r;
-    if (tok >= M || n >= N) continue;
-    float v = 0.f;
-    for (int sp = 0; sp < nsplit; ++sp) v += __ldcg(&part[((int64_t)sp * M + tok) * N + n]);
-    if (bias) v += __half2float(bias[n]);
-    z[(int64_t)tok * N + n] = __float2half_rn(v);
+  // software pipeline over the flattened (row tile, k round) sequence: the packed words of step i+1 are
+  // in flight while step i is expanded and multiplied
+  SbRegs<BITS> cur[RBC], nxt[RBC];
+  auto fetch = [&](int tile, int round, SbRegs<BITS> (&dst)[RBC]) {
+    const int ksb = ksb0 + round * SK_WARPS + warp;
+    const int kk = min(ksb, ksb1 - 1);
+#pragma unroll
+    for (int r = 0; r < RBC; ++r) {
+      int rb = min(tile * RBC + r, NRB - 1);              // tail tile: re-read a valid block, masked at the store
+      load_sb<BITS>(q + ((int64_t)rb * KSB + kk) * sb_words(BITS), lane, dst[r]);
+    }
+  };
+
+  int tile = blockIdx.x;
+  if (tile < ntiles) fetch(tile, 0, cur);
+  for (; tile < ntiles; tile += gridDim.x) {
+    float acc[RBC][NT8][4];
+#pragma unroll
+    for (int a = 0; a < RBC; ++a)
+#pragma unroll
+      for (int b = 0; b < NT8; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+    for (int round = 0; round < rounds; ++round) {
+      // prefetch the next step (next k round, or the first round of this CTA's next row tile)
+      {
+        int nt = tile, nr = round + 1;
+        if (nr == rounds) { nr = 0; nt = tile + gridDim.x; }
+        if (nt < ntiles) fetch(nt, nr, nxt);
+      }
+      const int ksb = ksb0 + round * SK_WARPS + warp;
+      if (ksb < ksb1) {
+        const __half* xk = xs + (ksb - ksb0) * 128 + 8 * t;
+        auto do_chunk = [&](auto chc) {
+          constexpr int CH = decltype(chc)::value;
+          uint32_t xb[NT8][4];
+#pragma unroll
+          for (int nt = 0; nt < NT8; ++nt) {
+            uint4 v = *reinterpret_cast<const uint4*>(xk + (nt * 8 + g) * xld + CH * 32);
+            xb[nt][0] = v.x; xb[nt][1] = v.y; xb[nt][2] = v.z; xb[nt][3] = v.w;
+          }
+#pragma unroll
+          for (int r = 0; r < RBC; ++r) {
+            uint32_t h[8];
+            expand_sb_chunk<BITS, CH>(cur[r], h);
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              uint32_t a[4] = {h[4 * s], h[4 * s + 1], h[4 * s + 2], h[4 * s + 3]};
+#pragma unroll
+              for (int nt = 0; nt < NT8; ++nt) {
+                uint32_t b[2] = {xb[nt][2 * s], xb[nt][2 * s + 1]};
+                mma16816(acc[r][nt], a, b);
+              }
+            }
+          }
+        };
+        do_chunk(std::integral_constant<int, 0>{});
+        do_chunk(std::integral_constant<int, 1>{});
+        do_chunk(std::integral_constant<int, 2>{});
+        do_chunk(std::integral_constant<int, 3>{});
+      }
+#pragma unroll
+      for (int r = 0; r < RBC; ++r) cur[r] = nxt[r];
+    }
+
+    // ---- reduce the 8 warps: red[warp][tok][row] ----
+#pragma unroll
+    for (int r = 0; r < RBC; ++r)
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) {
+        float* b = red + (warp * TOK + nt * 8 + 2 * t) * RLD + r * 16 + g;
+        b[0] = acc[r][nt][0];
+        b[RLD] = acc[r][nt][1];
+        b[8] = acc[r][nt][2];
+        b[RLD + 8] = acc[r][nt][3];
+      }
+    __syncthreads();
+
+    const int n0 = tile * ROWS;
+    for (int e = tid; e < TOK * ROWS; e += SK_WARPS * 32) {
+      int tok = e / ROWS, r = e % ROWS;
+      int n = n0 + r;
+      if (tok >= M || n >= N) continue;
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < SK_WARPS; ++w) s += red[(w * TOK + tok) * RLD + r];
+      float sc = scales[n];
+      float v = sc * (float)(1 << BITS) * s;
+      if (!symmetric) v += (sc * (0.5f * (float)((1 << BITS) - 1)) - zeros[n]) * xsum_s[tok];
+      if (direct) {
+        if (bias) v += __half2float(bias[n]);
+        z[(int64_t)tok * N + n] = __float2half_rn(v);
+      } else {
+        part[((int64_t)blockIdx.y * M + tok) * N + n] = v;
+      }
+    }
+    if (!direct) {
+      // ---- K splits: the last CTA to finish this row tile sums the partials in split order ----
+      __threadfence();
+      __syncthreads();
+      if (tid == 0) {
+        int prev = atomicAdd(&counters[tile], 1);
+        s_last = (prev == nsplit - 1);
+        if (s_last) counters[tile] = 0;                   // leave the header zeroed for the next call
+      }
+      __syncthreads();
+      if (s_last) {
+        __threadfence();
+        for (int e = tid; e < TOK * ROWS; e += SK_WARPS * 32) {
+          int tok = e / ROWS, r = e % ROWS;
+          int n = n0 + r;
+          if (tok >= M || n >= N) continue;
+          float v = 0.f;
+          for (int sp = 0; sp < nsplit; ++sp) v += __ldcg(&part[((int64_t)sp * M + tok) * N + n]);
+          if (bias) v += __half2float(bias[n]);
+          z[(int64_t)tok * N + n] = __float2half_rn(v);
+        }
+      }
+    }
+    __syncthreads();                                      // red[] is reused by the next row tile
   }
 }
+
+int num_sms();
+static int sk_num_sms() { return num_sms(); }
 
 template <int BITS, int NT8, int RBC>
 static int launch_skinny(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M,
@@ -205,7 +235,14 @@ static int launch_skinny(const QuipLinearDesc* d, const __half* x, const __half*
   auto kern = qgemm_skinny_kernel<BITS, NT8, RBC>;
   QUIP_CHECK_ARG(smem <= 220 * 1024, "skinny kernel: K slice too large (%zu B of shared memory)", smem);
   QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(ceil_div(d->N, ROWS), ksplit);
+  // persistent in the row dimension: ~2 CTAs per SM in total, each looping over row tiles with its K slice of
+  // the activations staged once
+  int tiles = ceil_div(d->N, ROWS);
+  QUIP_CHECK_ARG(ksplit == 1 || tiles <= 4096, "skinny kernel: too many row tiles (%d) for split-K counters", tiles);
+  int gx = ceil_div(2 * sk_num_sms(), ksplit);
+  if (gx > tiles) gx = tiles;
+  if (gx < 1) gx = 1;
+  dim3 grid(gx, ksplit);
   kern<<<grid, SK_WARPS * 32, smem, s>>>(reinterpret_cast<const uint32_t*>(d->qweight), x, d->scales, d->zeros, bias,
                                          z, M, d->K, d->N, per, (d->flags & QUIP_FLAG_SYMMETRIC) ? 1 : 0, part,
                                          counters);

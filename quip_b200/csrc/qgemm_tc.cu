@@ -9,10 +9,11 @@
 //         swizzle, out-of-bounds rows zero-filled so ragged M needs no special case);
 //   epilogue: z[m][n] = P_n * D + R_n * xsum[m] (+ bias_n) -> fp16, straight from tcgen05.ld registers.
 //
-// Warp roles (320 threads, one persistent CTA per SM, static tile schedule):
+// Warp roles (448 threads, one persistent CTA per SM, static tile schedule):
 //   warp 0      TMA producer            warp 1      TMEM alloc + MMA issuer (one lane)
 //   warps 2-5   epilogue (TMEM lane quarter = warp % 4)
-//   warps 6-9   weight producers: 128-bit loads of packed words -> registers -> fp16 -> smem
+//   warps 6-13  weight producers (2 groups of 4 alternating k super-blocks): 128-bit loads of packed
+//               words -> registers -> fp16 -> smem
 // Pipelines: smem ring full[s]/empty[s] (TMA + 4 producer warps -> MMA -> tcgen05.commit), and a
 // double-buffered TMEM accumulator tmem_full[a]/tmem_empty[a] (MMA -> epilogue).
 #include "tc_common.cuh"
@@ -174,50 +175,11 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
   } else if (!DENSE) {
     // ================= weight producers: packed words -> fp16 operand tile =================
-    const int pw = warp - 6;                       // 0..3
-    const int g = lane & 7, t = lane >> 3;         // 8 consecutive lanes = 8 rows g: conflict-free st.shared.v4
-    const int l = 4 * g + t;                       // "lane" index of the native layout
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int rb_base = ((tile % per_blk) % tiles_n) * (TC_BM / 16);
-      const int NRB = N >> 4;
-      // this thread serves row blocks pw and pw+4 of the tile
-      const int rbl0 = pw, rbl1 = pw + 4;
-      const bool v0 = rb_base + rbl0 < NRB, v1 = rb_base + rbl1 < NRB;
-      const uint32_t* q0 = q + (int64_t)(rb_base + rbl0) * KSB * sb_words(BITS);
-      const uint32_t* q1 = q + (int64_t)(rb_base + rbl1) * KSB * sb_words(BITS);
-      TcWords<BITS> c0, c1, n0, n1;                // current and next super-block (software prefetch)
-      tc_load_words<BITS>(q0, l, c0, v0);
-      tc_load_words<BITS>(q1, l, c1, v1);
-      for (int ksb = 0; ksb < KSB; ++ksb) {
-        const bool more = ksb + 1 < KSB;
-        tc_load_words<BITS>(q0 + (int64_t)(ksb + 1) * sb_words(BITS), l, n0, v0 && more);
-        tc_load_words<BITS>(q1 + (int64_t)(ksb + 1) * sb_words(BITS), l, n1, v1 && more);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {     // two 64-k stages per 128-k super-block
-          mbar_wait(&empty[s], ph ^ 1u);
-          const uint32_t a_tile = smem_base + (uint32_t)(s * C::STAGE_BYTES);
-          if (half == 0) {
-            tc_store_chunk<BITS, 0>(c0, a_tile, rbl0, g, t, v0);
-            tc_store_chunk<BITS, 1>(c0, a_tile, rbl0, g, t, v0);
-            tc_store_chunk<BITS, 0>(c1, a_tile, rbl1, g, t, v1);
-            tc_store_chunk<BITS, 1>(c1, a_tile, rbl1, g, t, v1);
-          } else {
-            tc_store_chunk<BITS, 2>(c0, a_tile, rbl0, g, t, v0);
-            tc_store_chunk<BITS, 3>(c0, a_tile, rbl0, g, t, v0);
-            tc_store_chunk<BITS, 2>(c1, a_tile, rbl1, g, t, v1);
-            tc_store_chunk<BITS, 3>(c1, a_tile, rbl1, g, t, v1);
-          }
-          fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&full[s]);
-          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
-        }
-        c0 = n0;
-        c1 = n1;
-      }
-    }
+    const int pw = (warp - 6) & 3, grp = (warp - 6) >> 2;
+    weight_producer_loop<BITS, C::STAGES, C::STAGE_BYTES>(
+        pw, grp, lane, q, KSB, N, empty, smem_base, (int)blockIdx.x, (int)gridDim.x, num_tiles,
+        [&](int tile) { return ((tile % per_blk) % tiles_n) * (TC_BM / 16); },
+        [&](int s) { mbar_arrive(&full[s]); });
   }
 
   tc_fence_before();

@@ -11,6 +11,9 @@
 //   empty[s]      in both CTAs; tcgen05.commit multicast from the leader frees the stage in both
 //   tmem_full[a]  in both CTAs; commit multicast
 //   tmem_empty[a] leader only; 4 + 4 epilogue warps (peer's arrive remotely)
+// All waits are plain CTA-scope try_waits on barriers in the waiter's own shared memory (as CUTLASS' 2-SM
+// kernels do): a cluster-scope acquire compiles to MEMBAR.ALL.GPU + CCTL.IVALL after every wait, which
+// drains the producers' in-flight prefetches and the epilogue's stores (measured: 2x slower).
 #include "tc_common.cuh"
 
 namespace quip {
@@ -41,21 +44,7 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t cta_addr, uint32_t rank) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar), done = 0, spins = 0;
-  while (true) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (done) break;
-    if (++spins > TC_WATCHDOG) __trap();
-  }
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t smem_dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
                                                 int c1) {
@@ -137,7 +126,7 @@ qgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __r
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int m0 = (tile / tiles_n) * C::BN + (int)rank * C::HALF;
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait_cluster(&empty[s], ph ^ 1u);
+          mbar_wait(&empty[s], ph ^ 1u);
           const uint32_t leader_full = mapa_u32(smem_u32(&full[s]), 0);
           if (leader) mbar_arrive_expect_tx(&full[s], 2 * C::B_BYTES);
           tma_load_2d_2sm(smem_base + (uint32_t)(s * C::STAGE_BYTES + C::A_BYTES), &tmap_x, leader_full, kb * TC_BK, m0);
@@ -155,11 +144,13 @@ qgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __r
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
         const int as = it & 1;
         const uint32_t aph = (uint32_t)(it >> 1) & 1u;
-        mbar_wait_cluster(&tmem_empty[as], aph ^ 1u);
+        if (lane == 0) mbar_wait(&tmem_empty[as], aph ^ 1u);
+        __syncwarp();
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(as * C::BN);
         for (int kb = 0; kb < KB; ++kb) {
-          mbar_wait_cluster(&full[s], ph);
+          if (lane == 0) mbar_wait(&full[s], ph);
+          __syncwarp();
           tc_fence_after();
           if (lane == 0) {
             const uint32_t a_addr = smem_base + (uint32_t)(s * C::STAGE_BYTES);
@@ -192,7 +183,7 @@ qgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __r
         if (!symmetric) Rn = sc * (0.5f * (float)((1 << BITS) - 1)) - zeros[n];
         if (bias) bn = __half2float(bias[n]);
       }
-      mbar_wait_cluster(&tmem_full[as], aph);
+      mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * C::BN);
 #pragma unroll 1
@@ -221,52 +212,15 @@ qgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __r
     }
   } else {
     // ================= weight producers: this CTA's 128 rows =================
-    const int pw = warp - 6;
-    const int g = lane & 7, t = lane >> 3;
-    const int l = 4 * g + t;
-    int s = 0;
-    uint32_t ph = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const int rb_base = (tile % tiles_n) * (2 * TC_BM / 16) + (int)rank * (TC_BM / 16);
-      const int NRB = N >> 4;
-      const int rbl0 = pw, rbl1 = pw + 4;
-      const bool v0 = rb_base + rbl0 < NRB, v1 = rb_base + rbl1 < NRB;
-      const uint32_t* q0 = q + (int64_t)(rb_base + rbl0) * KSB * sb_words(BITS);
-      const uint32_t* q1 = q + (int64_t)(rb_base + rbl1) * KSB * sb_words(BITS);
-      TcWords<BITS> c0, c1, n0, n1;
-      tc_load_words<BITS>(q0, l, c0, v0);
-      tc_load_words<BITS>(q1, l, c1, v1);
-      for (int ksb = 0; ksb < KSB; ++ksb) {
-        const bool more = ksb + 1 < KSB;
-        tc_load_words<BITS>(q0 + (int64_t)(ksb + 1) * sb_words(BITS), l, n0, v0 && more);
-        tc_load_words<BITS>(q1 + (int64_t)(ksb + 1) * sb_words(BITS), l, n1, v1 && more);
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          mbar_wait_cluster(&empty[s], ph ^ 1u);
-          const uint32_t a_tile = smem_base + (uint32_t)(s * C::STAGE_BYTES);
-          if (half == 0) {
-            tc_store_chunk<BITS, 0>(c0, a_tile, rbl0, g, t, v0);
-            tc_store_chunk<BITS, 1>(c0, a_tile, rbl0, g, t, v0);
-            tc_store_chunk<BITS, 0>(c1, a_tile, rbl1, g, t, v1);
-            tc_store_chunk<BITS, 1>(c1, a_tile, rbl1, g, t, v1);
-          } else {
-            tc_store_chunk<BITS, 2>(c0, a_tile, rbl0, g, t, v0);
-            tc_store_chunk<BITS, 3>(c0, a_tile, rbl0, g, t, v0);
-            tc_store_chunk<BITS, 2>(c1, a_tile, rbl1, g, t, v1);
-            tc_store_chunk<BITS, 3>(c1, a_tile, rbl1, g, t, v1);
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            if (leader) mbar_arrive(&full[s]);
-            else mbar_arrive_cluster(mapa_u32(smem_u32(&full[s]), 0));
-          }
-          if (++s == C::STAGES) { s = 0; ph ^= 1u; }
-        }
-        c0 = n0;
-        c1 = n1;
-      }
-    }
+    const int pw = (warp - 6) & 3, grp = (warp - 6) >> 2;
+    const uint32_t leader_full0 = mapa_u32(smem_u32(&full[0]), 0);
+    weight_producer_loop<BITS, C::STAGES, C::STAGE_BYTES>(
+        pw, grp, lane, q, KSB, N, empty, smem_base, cluster_id, num_clusters, num_tiles,
+        [&](int tile) { return (tile % tiles_n) * (2 * TC_BM / 16) + (int)rank * (TC_BM / 16); },
+        [&](int s) {
+          if (leader) mbar_arrive(&full[s]);
+          else mbar_arrive_cluster(leader_full0 + (uint32_t)(s * 8));
+        });
   }
 
   tc_fence_before();

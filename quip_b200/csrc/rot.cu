@@ -17,6 +17,9 @@
 
 namespace quip {
 
+int g_gather_rows = 0;        // quip_config("gather_rows", R)
+int g_pass_min_tiles = 4;     // quip_config("pass_min_tiles", t): token tiles per CTA in the small-block passes
+
 // ----------------------------------------------------------------------------------------------
 // R rows per CTA share one read of the index vector (4 bytes/feature, twice the fp16 row itself)
 template <int R>
@@ -402,11 +405,14 @@ extern "C" int quip_gather(const void* in, void* out, int64_t M, int32_t n, cons
   const __half* i = (const __half*)in;
   __half* o = (__half*)out;
   const __half* b = (const __half*)bias;
-  // rows per CTA: as many as fit ~96 KB of shared memory (2 CTAs / SM), fewer when M is small
+  // rows per CTA: share the index vector across rows, but keep several waves of CTAs so that one CTA's load
+  // phase overlaps another's permute phase
   const size_t row = (size_t)n * sizeof(__half);
-  if (M >= 8 * 148 && 8 * row <= 96 * 1024) return launch_gather<8>(i, o, M, n, idx, scale, b, s);
-  if (M >= 4 * 148 && 4 * row <= 96 * 1024) return launch_gather<4>(i, o, M, n, idx, scale, b, s);
-  if (M >= 2 * 148 && 2 * row <= 96 * 1024) return launch_gather<2>(i, o, M, n, idx, scale, b, s);
+  int R = g_gather_rows > 0 ? g_gather_rows : 4;
+  while (R > 1 && (M < (int64_t)R * 592 || R * row > 96 * 1024)) R >>= 1;
+  if (R >= 8) return launch_gather<8>(i, o, M, n, idx, scale, b, s);
+  if (R >= 4) return launch_gather<4>(i, o, M, n, idx, scale, b, s);
+  if (R >= 2) return launch_gather<2>(i, o, M, n, idx, scale, b, s);
   return launch_gather<1>(i, o, M, n, idx, scale, b, s);
 }
 

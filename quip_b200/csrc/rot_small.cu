@@ -55,13 +55,13 @@ __device__ __forceinline__ void load_bfrags(const __half* __restrict__ f, int p,
 }
 
 // D[tok][i] = sum_j A[tok][j] F[i][j] for one block tile (TM tokens), in place
-template <int P>
+template <int P, int TM>
 __device__ __forceinline__ void mul_tile_inplace(__half* tile, const uint32_t (&bf)[FCfg<P>::KS][FCfg<P>::NT][2],
                                                  int lane) {
   using C = FCfg<P>;
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
-  for (int mt = 0; mt < C::TM / 16; ++mt) {
+  for (int mt = 0; mt < TM / 16; ++mt) {
     uint32_t a[C::KS][4];
 #pragma unroll
     for (int ks = 0; ks < C::KS; ++ks)
@@ -81,7 +81,7 @@ __device__ __forceinline__ void mul_tile_inplace(__half* tile, const uint32_t (&
 // ------------------------------------------------------------------------------------------------
 constexpr int PC_WARPS = 4, PC_STAGES = 3;
 
-template <int P>
+template <int P, bool AFFINE>
 __global__ void __launch_bounds__(PC_WARPS * 32)
 pass_contig_kernel(const __half* __restrict__ in, __half* __restrict__ out, const __half* __restrict__ F, int64_t M,
                    int n, int p, int nblk, int shared, int tok_chunk) {
@@ -107,16 +107,43 @@ pass_contig_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
   }
   const int w8 = C::BPW * p / 8;                                // 16-byte chunks per token row segment
   const int64_t col0 = (int64_t)blk0 * p;
+  // The (token, chunk) -> address map is the same for every tile.  When 32 % w8 == 0 (p | 64) it is affine in
+  // the per-lane step r (token += 32/w8, same chunk), so the divisions are resolved once; other block sizes
+  // take the generic path.
+  constexpr int MAXC = (C::TM * C::BPW * P / 8 + 31) / 32;      // chunks per lane per tile (upper bound)
+  constexpr bool affine = AFFINE;                             // host guarantees 32 % w8 == 0
+  const int tstep = affine ? 32 / w8 : 0;
+  auto chunk = [&](int r, int& soff, int& goff, int& tok) -> bool {
+    int c = lane + r * 32, q, bl, j;
+    if (affine) {
+      tok = lane / w8 + r * tstep; q = lane % w8;
+    } else {
+      if (c >= C::TM * w8) return false;
+      tok = c / w8; q = c % w8;
+    }
+    if (tok >= C::TM) return false;
+    bl = (q * 8) / p; j = (q * 8) % p;
+    if (blk0 + bl >= nblk) return false;
+    soff = (bl * C::TM + tok) * C::LD + j;
+    goff = tok * n + q * 8;
+    return true;
+  };
+  int s0 = 0, g0 = 0, t0 = 0;
+  const bool ok0 = chunk(0, s0, g0, t0);
 
   auto issue = [&](int tile) {
     __half* dst = ring + (size_t)(tile % PC_STAGES) * TILE;
     const int64_t m0 = m_begin + (int64_t)tile * C::TM;
-    for (int c = lane; c < C::TM * w8; c += 32) {
-      const int tok = c / w8, q = c % w8;
-      const int bl = (q * 8) / p, j = (q * 8) % p;
-      const bool valid = (m0 + tok < m_end) && (blk0 + bl < nblk);
-      const __half* src = in + (valid ? ((m0 + tok) * n + col0 + q * 8) : 0);
-      cp_async16s(&dst[(bl * C::TM + tok) * C::LD + j], src, valid);
+    const __half* src0 = in + m0 * n + col0;
+#pragma unroll
+    for (int r = 0; r < MAXC; ++r) {
+      int so, go, tk;
+      bool ok;
+      if (affine) { ok = ok0 && (t0 + r * tstep < C::TM); so = s0 + r * tstep * C::LD; go = g0 + r * tstep * n; tk = t0 + r * tstep; }
+      else ok = chunk(r, so, go, tk);
+      if (!ok) continue;
+      const bool valid = m0 + tk < m_end;
+      cp_async16s(&dst[so], valid ? (src0 + go) : in, valid);
     }
   };
 
@@ -132,15 +159,17 @@ pass_contig_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
     asm volatile("cp.async.commit_group;");
     __half* tile = ring + (size_t)(it % PC_STAGES) * TILE;
 #pragma unroll
-    for (int bb = 0; bb < C::BPW; ++bb) mul_tile_inplace<P>(tile + bb * C::TM * C::LD, bf[bb], lane);
+    for (int bb = 0; bb < C::BPW; ++bb) mul_tile_inplace<P, C::TM>(tile + bb * C::TM * C::LD, bf[bb], lane);
     __syncwarp();
     const int64_t m0 = m_begin + (int64_t)it * C::TM;
-    for (int c = lane; c < C::TM * w8; c += 32) {
-      const int tok = c / w8, q = c % w8;
-      const int bl = (q * 8) / p, j = (q * 8) % p;
-      if ((m0 + tok < m_end) && (blk0 + bl < nblk))
-        *reinterpret_cast<uint4*>(out + (m0 + tok) * n + col0 + q * 8) =
-            *reinterpret_cast<const uint4*>(&tile[(bl * C::TM + tok) * C::LD + j]);
+    __half* dst0 = out + m0 * n + col0;
+#pragma unroll
+    for (int r = 0; r < MAXC; ++r) {
+      int so, go, tk;
+      bool ok;
+      if (affine) { ok = ok0 && (t0 + r * tstep < C::TM); so = s0 + r * tstep * C::LD; go = g0 + r * tstep * n; tk = t0 + r * tstep; }
+      else ok = chunk(r, so, go, tk);
+      if (ok && m0 + tk < m_end) *reinterpret_cast<uint4*>(dst0 + go) = *reinterpret_cast<const uint4*>(&tile[so]);
     }
     __syncwarp();
   }
@@ -149,24 +178,25 @@ pass_contig_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
 
 // ------------------------------------------------------------------------------------------------
 constexpr int PS_WARPS = 8;
+constexpr int PS_TM = 16;        // tokens per tile of the strided kernel (keeps the prefetch registers small)
 
-template <int P>
+template <int P, bool AFFINE>
 __global__ void __launch_bounds__(PS_WARPS * 32, 2)
 pass_strided_kernel(const __half* __restrict__ in, __half* __restrict__ out, const __half* __restrict__ F, int64_t M,
                     int n, int p, int nblk, int shared, int tok_chunk) {
   using C = FCfg<P>;
   constexpr int GB = PS_WARPS * C::BPW;                         // blocks per CTA
   constexpr int CG = GB / 8;                                    // 16-byte chunks per (tok, j)
-  constexpr int TILE = GB * C::TM * C::LD;                      // halves per buffer
-  constexpr int NCH = (C::TM * P * CG + PS_WARPS * 32 - 1) / (PS_WARPS * 32);
+  constexpr int TILE = GB * PS_TM * C::LD;                      // halves per buffer
+  constexpr int NCH = (PS_TM * P * CG + PS_WARPS * 32 - 1) / (PS_WARPS * 32);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* T = reinterpret_cast<__half*>(smem_raw);              // [2][GB][TM][LD]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int b0 = blockIdx.x * GB;
   const int64_t m_begin = (int64_t)blockIdx.y * tok_chunk;
   const int64_t m_end = m_begin + tok_chunk < M ? m_begin + tok_chunk : M;
-  const int ntiles = (int)((m_end - m_begin + C::TM - 1) / C::TM);
-  const int nchunks = C::TM * p * CG;
+  const int ntiles = (int)((m_end - m_begin + PS_TM - 1) / PS_TM);
+  const int nchunks = PS_TM * p * CG;
 
   uint32_t bf[C::BPW][C::KS][C::NT][2];
 #pragma unroll
@@ -176,23 +206,49 @@ pass_strided_kernel(const __half* __restrict__ in, __half* __restrict__ out, con
   }
   if (P != p) {
     const int padw = P - p;
-    for (int c = tid; c < 2 * GB * C::TM * padw; c += PS_WARPS * 32)
+    for (int c = tid; c < 2 * GB * PS_TM * padw; c += PS_WARPS * 32)
       T[(c / padw) * C::LD + p + c % padw] = __float2half(0.f);
   }
 
+  // per-thread chunk map (tile-invariant).  With 256 % (p*CG) == 0 it is affine in r (token += 256/(p*CG), same
+  // (j, block run)); other block sizes take the generic path with divisions.
+  const int ppc = p * CG;
+  constexpr bool affine = AFFINE;                             // host guarantees 256 % (p*CG) == 0
+  const int tstep = affine ? (PS_WARPS * 32) / ppc : 0;
+  auto chunk = [&](int r, int& soff, int& goff, int& tok) -> bool {
+    int c8, j;
+    if (affine) {
+      tok = tid / ppc + r * tstep; c8 = tid % CG; j = (tid / CG) % p;
+    } else {
+      const int c = tid + r * PS_WARPS * 32;
+      if (c >= nchunks) return false;
+      c8 = c % CG; j = (c / CG) % p; tok = c / ppc;
+    }
+    if (tok >= PS_TM) return false;
+    const int blk = b0 + c8 * 8;
+    if (blk >= nblk) return false;
+    soff = ((c8 * 8) * PS_TM + tok) * C::LD + j;
+    goff = tok * n + j * nblk + blk;
+    return true;
+  };
+  int s0 = 0, g0 = 0, t0 = 0;
+  const bool ok0 = chunk(0, s0, g0, t0);
+#define QUIP_CHUNK(r, so, go, tk, ok)                                                                       \
+  int so, go, tk;                                                                                          \
+  bool ok;                                                                                                 \
+  if (affine) { tk = t0 + (r) * tstep; ok = ok0 && tk < PS_TM; so = s0 + (r) * tstep * C::LD; go = g0 + (r) * tstep * n; } \
+  else ok = chunk(r, so, go, tk);
+  constexpr int BSTRIDE = PS_TM * C::LD;                        // smem distance between adjacent blocks' tiles
+
   uint4 pre[NCH];
   auto prefetch = [&](int tile) {
-    const int64_t m0 = m_begin + (int64_t)tile * C::TM;
+    const int64_t m0 = m_begin + (int64_t)tile * PS_TM;
+    const __half* src0 = in + m0 * n;
 #pragma unroll
     for (int r = 0; r < NCH; ++r) {
-      const int c = tid + r * PS_WARPS * 32;
       pre[r] = make_uint4(0, 0, 0, 0);
-      if (c < nchunks) {
-        const int c8 = c % CG, j = (c / CG) % p, tok = c / (CG * p);
-        const int blk = b0 + c8 * 8;
-        if (m0 + tok < m_end && blk < nblk)
-          pre[r] = ldg_nc_v4(in + (m0 + tok) * n + (int64_t)j * nblk + blk);
-      }
+      QUIP_CHUNK(r, so, go, tk, ok)
+      if (ok && m0 + tk < m_end) pre[r] = ldg_nc_v4(src0 + go);
     }
   };
 
@@ -201,41 +257,43 @@ pass_strided_kernel(const __half* __restrict__ in, __half* __restrict__ out, con
     __half* buf = T + (size_t)(it & 1) * TILE;
 #pragma unroll
     for (int r = 0; r < NCH; ++r) {
-      const int c = tid + r * PS_WARPS * 32;
-      if (c < nchunks) {
-        const int c8 = c % CG, j = (c / CG) % p, tok = c / (CG * p);
+      QUIP_CHUNK(r, so, go, tk, ok)
+      if (ok) {
         const __half* h = reinterpret_cast<const __half*>(&pre[r]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) buf[((c8 * 8 + i) * C::TM + tok) * C::LD + j] = h[i];
+        for (int i = 0; i < 8; ++i) buf[so + i * BSTRIDE] = h[i];
       }
     }
     __syncthreads();
     if (it + 1 < ntiles) prefetch(it + 1);
 #pragma unroll
     for (int bb = 0; bb < C::BPW; ++bb)
-      mul_tile_inplace<P>(buf + (size_t)((warp * C::BPW + bb) * C::TM) * C::LD, bf[bb], lane);
+      mul_tile_inplace<P, PS_TM>(buf + (size_t)((warp * C::BPW + bb) * PS_TM) * C::LD, bf[bb], lane);
     __syncthreads();
-    const int64_t m0 = m_begin + (int64_t)it * C::TM;
-    for (int c = tid; c < nchunks; c += PS_WARPS * 32) {
-      const int c8 = c % CG, j = (c / CG) % p, tok = c / (CG * p);
-      const int blk = b0 + c8 * 8;
-      if (m0 + tok < m_end && blk < nblk) {
+    const int64_t m0 = m_begin + (int64_t)it * PS_TM;
+    __half* dst0 = out + m0 * n;
+#pragma unroll
+    for (int r = 0; r < NCH; ++r) {
+      QUIP_CHUNK(r, so, go, tk, ok)
+      if (ok && m0 + tk < m_end) {
         __align__(16) __half h[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = buf[((c8 * 8 + i) * C::TM + tok) * C::LD + j];
-        *reinterpret_cast<uint4*>(out + (m0 + tok) * n + (int64_t)j * nblk + blk) = *reinterpret_cast<const uint4*>(h);
+        for (int i = 0; i < 8; ++i) h[i] = buf[so + i * BSTRIDE];
+        *reinterpret_cast<uint4*>(dst0 + go) = *reinterpret_cast<const uint4*>(h);
       }
     }
   }
+#undef QUIP_CHUNK
 }
 
 // ------------------------------------------------------------------------------------------------
+extern int g_pass_min_tiles;
 static int pick_tok_chunk(int64_t M, int gx, int tm) {
   // enough CTAs for ~2 per SM, but keep >= 4 tiles per CTA when M allows so the register-resident
   // factors are amortised
   int64_t want_gy = (296 + gx - 1) / gx;
   int64_t chunk = (M + want_gy - 1) / want_gy;
-  if (chunk < 4 * tm) chunk = 4 * tm;
+  if (chunk < (int64_t)g_pass_min_tiles * tm) chunk = (int64_t)g_pass_min_tiles * tm;
   chunk = (chunk + tm - 1) / tm * tm;
   return (int)(chunk < (int64_t)tm ? tm : chunk);
 }
@@ -248,7 +306,8 @@ static int launch_fast(const QuipPass* ps, const __half* in, __half* out, int64_
     const int gx = ceil_div(ps->nblk, PC_WARPS * C::BPW);
     const int tok_chunk = pick_tok_chunk(M, gx, C::TM);
     size_t smem = (size_t)PC_WARPS * PC_STAGES * C::BPW * C::TM * C::LD * sizeof(__half);
-    auto kern = pass_contig_kernel<P>;
+    const bool affine = (32 % (C::BPW * ps->p / 8)) == 0;
+    auto kern = affine ? pass_contig_kernel<P, true> : pass_contig_kernel<P, false>;
     if (smem > 48 * 1024) QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(gx, ceil_div(M, tok_chunk));
     kern<<<grid, PC_WARPS * 32, smem, s>>>(in, out, F, M, n, ps->p, ps->nblk, ps->shared, tok_chunk);
@@ -256,9 +315,10 @@ static int launch_fast(const QuipPass* ps, const __half* in, __half* out, int64_
   } else {
     constexpr int GB = PS_WARPS * C::BPW;
     const int gx = ceil_div(ps->nblk, GB);
-    const int tok_chunk = pick_tok_chunk(M, gx, C::TM);
-    size_t smem = (size_t)2 * GB * C::TM * C::LD * sizeof(__half);
-    auto kern = pass_strided_kernel<P>;
+    const int tok_chunk = pick_tok_chunk(M, gx, PS_TM);
+    size_t smem = (size_t)2 * GB * PS_TM * C::LD * sizeof(__half);
+    const bool affine = ((PS_WARPS * 32) % (ps->p * (GB / 8))) == 0;
+    auto kern = affine ? pass_strided_kernel<P, true> : pass_strided_kernel<P, false>;
     if (smem > 48 * 1024) QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(gx, ceil_div(M, tok_chunk));
     kern<<<grid, PS_WARPS * 32, smem, s>>>(in, out, F, M, n, ps->p, ps->nblk, ps->shared, tok_chunk);

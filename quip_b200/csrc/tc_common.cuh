@@ -9,7 +9,8 @@ namespace quip {
 
 constexpr int TC_BM = 128;            // output rows per tile (MMA M)
 constexpr int TC_BK = 64;             // k per stage = one 128-byte swizzle atom of fp16
-constexpr int TC_THREADS = 320;
+constexpr int TC_PROD_GROUPS = 2;     // producer groups of 4 warps alternate k super-blocks
+constexpr int TC_THREADS = 192 + 128 * TC_PROD_GROUPS;
 constexpr uint32_t TC_WATCHDOG = 1u << 28;
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -137,5 +138,60 @@ __device__ __forceinline__ void tc_store_chunk(const TcWords<BITS>& r, uint32_t 
                : "memory");
 }
 
+
+// Weight-producer loop shared by the 1-CTA and 2-CTA kernels.  Group `grp` (4 warps) expands the k
+// super-blocks grp, grp+G, ... of every tile into stages 2*ksb and 2*ksb+1 of the global stage sequence.
+// Two groups are needed because fence.proxy.async compiles to MEMBAR.ALL.CTA, which also waits for the
+// thread's outstanding prefetch loads: with one group the ~1 us global-load latency would be exposed once
+// per super-block; alternating groups give each load two super-block periods to land.
+template <int BITS, int STAGES, int STAGE_BYTES, class RbBaseFn, class ArriveFn>
+__device__ __forceinline__ void weight_producer_loop(int pw, int grp, int lane, const uint32_t* __restrict__ q, int KSB,
+                                                     int N, uint64_t* empty, uint32_t smem_base, int first_tile,
+                                                     int tile_step, int num_tiles, RbBaseFn rb_base_of,
+                                                     ArriveFn arrive_full) {
+  const int g = lane & 7, t = lane >> 3;         // 8 consecutive lanes = 8 rows g: conflict-free st.shared.v4
+  const int l = 4 * g + t;                       // "lane" index of the native layout
+  const int NRB = N >> 4;
+  uint32_t it_base = 0;                          // stages consumed by earlier tiles
+  for (int tile = first_tile; tile < num_tiles; tile += tile_step, it_base += 2u * (uint32_t)KSB) {
+    const int rb_base = rb_base_of(tile);
+    const int rbl0 = pw, rbl1 = pw + 4;          // this thread serves row blocks pw and pw+4 of the tile
+    const bool v0 = rb_base + rbl0 < NRB, v1 = rb_base + rbl1 < NRB;
+    const uint32_t* q0 = q + (int64_t)(rb_base + rbl0) * KSB * sb_words(BITS);
+    const uint32_t* q1 = q + (int64_t)(rb_base + rbl1) * KSB * sb_words(BITS);
+    TcWords<BITS> c0, c1, n0, n1;
+    tc_load_words<BITS>(q0 + (int64_t)grp * sb_words(BITS), l, c0, v0 && grp < KSB);
+    tc_load_words<BITS>(q1 + (int64_t)grp * sb_words(BITS), l, c1, v1 && grp < KSB);
+    for (int ksb = grp; ksb < KSB; ksb += TC_PROD_GROUPS) {
+      const bool more = ksb + TC_PROD_GROUPS < KSB;
+      tc_load_words<BITS>(q0 + (int64_t)(ksb + TC_PROD_GROUPS) * sb_words(BITS), l, n0, v0 && more);
+      tc_load_words<BITS>(q1 + (int64_t)(ksb + TC_PROD_GROUPS) * sb_words(BITS), l, n1, v1 && more);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {     // two 64-k stages per 128-k super-block
+        const uint32_t it = it_base + 2u * (uint32_t)ksb + (uint32_t)half;
+        const int s = (int)(it % (uint32_t)STAGES);
+        const uint32_t ph = (it / (uint32_t)STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const uint32_t a_tile = smem_base + (uint32_t)(s * STAGE_BYTES);
+        if (half == 0) {
+          tc_store_chunk<BITS, 0>(c0, a_tile, rbl0, g, t, v0);
+          tc_store_chunk<BITS, 1>(c0, a_tile, rbl0, g, t, v0);
+          tc_store_chunk<BITS, 0>(c1, a_tile, rbl1, g, t, v1);
+          tc_store_chunk<BITS, 1>(c1, a_tile, rbl1, g, t, v1);
+        } else {
+          tc_store_chunk<BITS, 2>(c0, a_tile, rbl0, g, t, v0);
+          tc_store_chunk<BITS, 3>(c0, a_tile, rbl0, g, t, v0);
+          tc_store_chunk<BITS, 2>(c1, a_tile, rbl1, g, t, v1);
+          tc_store_chunk<BITS, 3>(c1, a_tile, rbl1, g, t, v1);
+        }
+        fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) arrive_full(s);
+      }
+      c0 = n0;
+      c1 = n1;
+    }
+  }
+}
 
 }  // namespace quip
