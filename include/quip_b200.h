@@ -94,7 +94,8 @@ int quip_qlinear_workspace_bytes(const QuipLinearDesc* d, int64_t M, size_t* out
 /* Building blocks (also exported for tests and micro-benchmarks). */
 /* z (M,N) fp16 = x2 (M,K) fp16 contracted with the packed matrix + affine epilogue (+bias if given).
  * xsum (M) fp32 row sums of x2, required unless QUIP_FLAG_SYMMETRIC.  path: 0 auto, 1 mma.sync skinny
- * kernel, 2 tcgen05 kernel, 3 tcgen05 2-CTA (cta_group::2) kernel. */
+ * kernel, 2 tcgen05 kernel, 3 tcgen05 2-CTA (cta_group::2) kernel, 4 tcgen05 TS-mode kernel (weights in
+ * TMEM, 2-bit only). */
 int quip_qgemm(const QuipLinearDesc* d, const void* x2, const float* xsum, const void* bias,
                void* z, int64_t M, int path, void* workspace, size_t workspace_bytes, void* stream);
 int quip_rowsum(const void* x, float* xsum, int64_t M, int32_t K, void* stream);
@@ -124,7 +125,8 @@ int quip_timing_enable(int on);
 int quip_timing_reset(void);
 int quip_timing_read(int path, double* total_ms, int64_t* launches, double* flops, double* bytes);
 
-/* Tuning knobs for ablations: "tc2" = 1 routes contractions with M > 128 to the 2-CTA tcgen05 kernel. */
+/* Tuning knobs for ablations: "tc2" / "ts" = 1 route contractions with M > 128 to the 2-CTA / TS-mode tcgen05
+ * kernels; "gather_rows", "pass_min_tiles" tune the un-projection kernels. */
 int quip_config(const char* key, int value);
 
 const char* quip_last_error(void);

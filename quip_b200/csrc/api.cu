@@ -32,11 +32,14 @@ int qgemm_tc(const QuipLinearDesc* d, const __half* x, const float* xsum, const 
              cudaStream_t s);
 int qgemm_tc2(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
               cudaStream_t s);
+int qgemm_ts(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
+             cudaStream_t s);
 
 extern int g_gather_rows, g_pass_min_tiles;   // rot.cu
 
 // tuning knobs (quip_config)
 static int g_use_tc2 = 0;        // route big-M contractions to the 2-CTA kernel
+static int g_use_ts = 0;         // route 2-bit big-M contractions to the TS-mode (A in TMEM) kernel
 
 constexpr size_t WS_HEADER = 16 * 1024;     // split-K arrival counters; must be zero on first use, left zero
 constexpr int SKINNY_MAX_M = 32;
@@ -95,7 +98,8 @@ static int run_qgemm_untimed(const QuipLinearDesc* d, const __half* x2, const fl
 
 static int run_qgemm(const QuipLinearDesc* d, const __half* x2, const float* xsum, const __half* bias, __half* z,
                      int64_t M, int path, unsigned char* ws, const WsPlan& p, cudaStream_t s) {
-  if (path == 0) path = M <= SKINNY_MAX_M ? 1 : ((g_use_tc2 && M > 128) ? 3 : 2);
+  if (path == 0)
+    path = M <= SKINNY_MAX_M ? 1 : ((g_use_ts && d->bits == 2 && M > 128) ? 4 : ((g_use_tc2 && M > 128) ? 3 : 2));
   if (!g_timing || g_timed.size() >= TIMED_MAX) return run_qgemm_untimed(d, x2, xsum, bias, z, M, path, ws, p, s);
   TimedLaunch t;
   if (!g_pool.empty()) {
@@ -105,7 +109,7 @@ static int run_qgemm(const QuipLinearDesc* d, const __half* x2, const float* xsu
     QUIP_CUDA(cudaEventCreate(&t.e0));
     QUIP_CUDA(cudaEventCreate(&t.e1));
   }
-  t.path = path == 3 ? 2 : path;
+  t.path = path >= 3 ? 2 : path;
   t.flops = 2.0 * (double)M * d->N * d->K;
   t.bytes = (double)d->N * d->K * d->bits / 8.0 + 2.0 * (double)M * (d->K + d->N);
   QUIP_CUDA(cudaEventRecord(t.e0, s));
@@ -131,6 +135,7 @@ static int run_qgemm_untimed(const QuipLinearDesc* d, const __half* x2, const fl
   const bool need_xsum = !(d->flags & QUIP_FLAG_SYMMETRIC);
   QUIP_CHECK_ARG(!need_xsum || xsum, "asymmetric grid needs the row sums of x");
   if (path == 3) return qgemm_tc2(d, x2, xsum, bias, z, (int)M, s);
+  if (path == 4) return qgemm_ts(d, x2, xsum, bias, z, (int)M, s);
   return qgemm_tc(d, x2, xsum, bias, z, (int)M, s);
 }
 
@@ -145,6 +150,7 @@ extern "C" int64_t quip_launch_count(void) { return g_launches.load(); }
 extern "C" int quip_config(const char* key, int value) {
   QUIP_CHECK_ARG(key != nullptr, "null key");
   if (!strcmp(key, "tc2")) { g_use_tc2 = value; return QUIP_OK; }
+  if (!strcmp(key, "ts")) { g_use_ts = value; return QUIP_OK; }
   if (!strcmp(key, "gather_rows")) { g_gather_rows = value; return QUIP_OK; }
   if (!strcmp(key, "pass_min_tiles")) { g_pass_min_tiles = value > 0 ? value : 1; return QUIP_OK; }
   set_error("quip_config: unknown key '%s'", key);
@@ -189,7 +195,7 @@ extern "C" int quip_qgemm(const QuipLinearDesc* d, const void* x2, const float* 
   if (int e = check_desc(d)) return e;
   QUIP_CHECK_ARG(x2 && z && M > 0 && M < (1ll << 31), "bad arguments");
   WsPlan p = plan_ws(d, M);
-  QUIP_CHECK_ARG(path >= 0 && path <= 3, "path must be 0..3");
+  QUIP_CHECK_ARG(path >= 0 && path <= 4, "path must be 0..4");
   if ((path == 1 || (path == 0 && M <= SKINNY_MAX_M)) && M <= SKINNY_MAX_M) {
     if (!workspace || workspace_bytes < p.total) {
       set_error("workspace too small: need %zu bytes, have %zu", p.total, workspace_bytes);

@@ -52,8 +52,10 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_n = (N + TC_BM - 1) / TC_BM;
-  const int tiles_m = (M + BN - 1) / BN;
+  // packed GEMM: 128 output rows (MMA M) x BN tokens (MMA N).  DENSE pass: 128 TOKENS (MMA M) x BN factor rows
+  // (MMA N), so every epilogue thread owns one token row and stores 64 contiguous bytes per 32 columns.
+  const int tiles_n = DENSE ? (N + BN - 1) / BN : (N + TC_BM - 1) / TC_BM;
+  const int tiles_m = DENSE ? (M + TC_BM - 1) / TC_BM : (M + BN - 1) / BN;
   const int per_blk = tiles_n * tiles_m;
   const int num_tiles = per_blk * nblk;
   const int KB = (K + TC_BK - 1) / TC_BK;
@@ -91,13 +93,17 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int blk = tile / per_blk, rr = tile % per_blk;
-        const int m0 = (rr / tiles_n) * BN, n0 = (rr % tiles_n) * TC_BM;
+        const int m0 = (rr / tiles_n) * (DENSE ? TC_BM : BN), n0 = (rr % tiles_n) * (DENSE ? BN : TC_BM);
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&empty[s], ph ^ 1u);
           mbar_arrive_expect_tx(&full[s], DENSE ? C::STAGE_BYTES : C::B_BYTES);
           unsigned char* stage = smem_gen + (size_t)s * C::STAGE_BYTES;
-          if (DENSE) tma_load_3d(stage, &tmap_a, &full[s], kb * TC_BK, n0, shared_factor ? 0 : blk);
-          tma_load_2d(stage + C::A_BYTES, &tmap_x, &full[s], blk * K + kb * TC_BK, m0);
+          if (DENSE) {
+            tma_load_2d(stage, &tmap_x, &full[s], blk * K + kb * TC_BK, m0);                     // A: 128 tokens
+            tma_load_3d(stage + C::A_BYTES, &tmap_a, &full[s], kb * TC_BK, n0, shared_factor ? 0 : blk);   // B: BN factor rows
+          } else {
+            tma_load_2d(stage + C::A_BYTES, &tmap_x, &full[s], kb * TC_BK, m0);
+          }
           if (++s == C::STAGES) { s = 0; ph ^= 1u; }
         }
       }
@@ -139,32 +145,66 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int as = it & 1;
       const uint32_t aph = (uint32_t)(it >> 1) & 1u;
       const int blk = tile / per_blk, rr = tile % per_blk;
-      const int n = (rr % tiles_n) * TC_BM + quarter * 32 + lane;
-      const int m0 = (rr / tiles_n) * BN;
-      float Pn = 1.f, Rn = 0.f, bn = 0.f;
-      if (!DENSE && n < N) {
-        float sc = scales[n];
-        Pn = sc * (float)(1 << BITS);
-        if (!symmetric) Rn = sc * (0.5f * (float)((1 << BITS) - 1)) - zeros[n];
-        if (bias) bn = __half2float(bias[n]);
-      }
-      __half* zcol = z + (int64_t)blk * N + n;
-      mbar_wait(&tmem_full[as], aph);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN);
+      if constexpr (DENSE) {
+        const int m = (rr / tiles_n) * TC_BM + quarter * 32 + lane;          // this thread's token
+        const int i0 = (rr % tiles_n) * BN;                                  // first factor row of the tile
+        __half* zrow = z + (int64_t)m * ldz + (int64_t)blk * N;
+        mbar_wait(&tmem_full[as], aph);
+        tc_fence_after();
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (n < N) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          const int i = i0 + c0;
+          if (m < M && i < N) {
+            if (i + 32 <= N) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const int m = m0 + c0 + c;
-            if (m < M) {
-              float v = Pn * __uint_as_float(r[c]) + bn;
-              if (!DENSE && !symmetric) v += Rn * __ldg(&xsum[m]);
-              zcol[(int64_t)m * ldz] = __float2half_rn(v);
+              for (int v4 = 0; v4 < 4; ++v4) {
+                uint4 o;
+                uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                  __half2 hv = __floats2half2_rn(__uint_as_float(r[8 * v4 + 2 * h]), __uint_as_float(r[8 * v4 + 2 * h + 1]));
+                  ow[h] = *reinterpret_cast<uint32_t*>(&hv);
+                }
+                *reinterpret_cast<uint4*>(zrow + i + 8 * v4) = o;
+              }
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c)
+                if (i + c < N) zrow[i + c] = __float2half_rn(__uint_as_float(r[c]));
+            }
+          }
+        }
+      } else {
+        const int n = (rr % tiles_n) * TC_BM + quarter * 32 + lane;
+        const int m0 = (rr / tiles_n) * BN;
+        float Pn = 1.f, Rn = 0.f, bn = 0.f;
+        if (n < N) {
+          float sc = scales[n];
+          Pn = sc * (float)(1 << BITS);
+          if (!symmetric) Rn = sc * (0.5f * (float)((1 << BITS) - 1)) - zeros[n];
+          if (bias) bn = __half2float(bias[n]);
+        }
+        __half* zcol = z + n;
+        mbar_wait(&tmem_full[as], aph);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (n < N) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const int m = m0 + c0 + c;
+              if (m < M) {
+                float v = Pn * __uint_as_float(r[c]) + bn;
+                if (!symmetric) v += Rn * __ldg(&xsum[m]);
+                zcol[(int64_t)m * ldz] = __float2half_rn(v);
+              }
             }
           }
         }
@@ -264,11 +304,11 @@ static int launch_tc_dense(const QuipPass* ps, const __half* in, __half* out, in
   using C = TcCfg<BN>;
   PFN_encodeTiled enc = get_encode();
   CUtensorMap tmx, tma;
-  if (int e = make_act_map(&tmx, in, M, n, BN)) return e;
+  if (int e = make_act_map(&tmx, in, M, n, TC_BM)) return e;       // 128 tokens per tile (MMA M)
   const int p = ps->p;
   cuuint64_t dims[3] = {(cuuint64_t)p, (cuuint64_t)p, (cuuint64_t)(ps->shared ? 1 : ps->nblk)};
   cuuint64_t strides[2] = {(cuuint64_t)p * sizeof(__half), (cuuint64_t)p * p * sizeof(__half)};
-  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM, 1};
+  cuuint32_t box[3] = {(cuuint32_t)TC_BK, (cuuint32_t)BN, 1};       // BN factor rows per tile (MMA N)
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(&tma, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)ps->factors, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -279,7 +319,7 @@ static int launch_tc_dense(const QuipPass* ps, const __half* in, __half* out, in
   }
   auto kern = qgemm_tc_kernel<2, BN, true>;
   QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM));
-  int tiles = ceil_div(p, TC_BM) * ceil_div(M, BN) * ps->nblk;
+  int tiles = ceil_div(p, BN) * ceil_div(M, TC_BM) * ps->nblk;
   int grid = tiles < num_sms() ? tiles : num_sms();
   kern<<<grid, TC_THREADS, C::SMEM, s>>>(tmx, tma, nullptr, nullptr, nullptr, nullptr, nullptr, out, M, p, p, 1,
                                          ps->nblk, ps->shared ? 1 : 0);
@@ -290,7 +330,7 @@ static int launch_tc_dense(const QuipPass* ps, const __half* in, __half* out, in
 int pass_big_tc(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s) {
   QUIP_CHECK_ARG(!ps->strided && ps->p % 8 == 0 && n % 8 == 0, "tcgen05 pass needs contiguous blocks, p %% 8 == 0");
   QUIP_CHECK_ARG((((uintptr_t)in | (uintptr_t)out | (uintptr_t)ps->factors) & 15) == 0, "tcgen05 pass: unaligned pointer");
-  return M > 128 ? launch_tc_dense<256>(ps, in, out, (int)M, n, s) : launch_tc_dense<128>(ps, in, out, (int)M, n, s);
+  return ps->p > 128 ? launch_tc_dense<256>(ps, in, out, (int)M, n, s) : launch_tc_dense<128>(ps, in, out, (int)M, n, s);
 }
 
 int qgemm_tc(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,

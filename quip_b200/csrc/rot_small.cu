@@ -177,18 +177,17 @@ pass_contig_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int PS_WARPS = 8;
 constexpr int PS_TM = 16;        // tokens per tile of the strided kernel (keeps the prefetch registers small)
 
-template <int P, bool AFFINE>
-__global__ void __launch_bounds__(PS_WARPS * 32, 2)
+template <int P, bool AFFINE, int W>
+__global__ void __launch_bounds__(W * 32, (W == 16 ? 1 : 2))
 pass_strided_kernel(const __half* __restrict__ in, __half* __restrict__ out, const __half* __restrict__ F, int64_t M,
                     int n, int p, int nblk, int shared, int tok_chunk) {
   using C = FCfg<P>;
-  constexpr int GB = PS_WARPS * C::BPW;                         // blocks per CTA
+  constexpr int GB = W * C::BPW;                         // blocks per CTA
   constexpr int CG = GB / 8;                                    // 16-byte chunks per (tok, j)
   constexpr int TILE = GB * PS_TM * C::LD;                      // halves per buffer
-  constexpr int NCH = (PS_TM * P * CG + PS_WARPS * 32 - 1) / (PS_WARPS * 32);
+  constexpr int NCH = (PS_TM * P * CG + W * 32 - 1) / (W * 32);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* T = reinterpret_cast<__half*>(smem_raw);              // [2][GB][TM][LD]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -206,7 +205,7 @@ pass_strided_kernel(const __half* __restrict__ in, __half* __restrict__ out, con
   }
   if (P != p) {
     const int padw = P - p;
-    for (int c = tid; c < 2 * GB * PS_TM * padw; c += PS_WARPS * 32)
+    for (int c = tid; c < 2 * GB * PS_TM * padw; c += W * 32)
       T[(c / padw) * C::LD + p + c % padw] = __float2half(0.f);
   }
 
@@ -214,13 +213,13 @@ pass_strided_kernel(const __half* __restrict__ in, __half* __restrict__ out, con
   // (j, block run)); other block sizes take the generic path with divisions.
   const int ppc = p * CG;
   constexpr bool affine = AFFINE;                             // host guarantees 256 % (p*CG) == 0
-  const int tstep = affine ? (PS_WARPS * 32) / ppc : 0;
+  const int tstep = affine ? (W * 32) / ppc : 0;
   auto chunk = [&](int r, int& soff, int& goff, int& tok) -> bool {
     int c8, j;
     if (affine) {
       tok = tid / ppc + r * tstep; c8 = tid % CG; j = (tid / CG) % p;
     } else {
-      const int c = tid + r * PS_WARPS * 32;
+      const int c = tid + r * W * 32;
       if (c >= nchunks) return false;
       c8 = c % CG; j = (c / CG) % p; tok = c / ppc;
     }
@@ -313,15 +312,17 @@ static int launch_fast(const QuipPass* ps, const __half* in, __half* out, int64_
     kern<<<grid, PC_WARPS * 32, smem, s>>>(in, out, F, M, n, ps->p, ps->nblk, ps->shared, tok_chunk);
     QUIP_LAUNCHED("pass_contig_kernel");
   } else {
-    constexpr int GB = PS_WARPS * C::BPW;
+    // 64-wide blocks: 16 warps = 16 adjacent blocks per CTA, so the strided runs are full 32-byte sectors
+    constexpr int W = (P == 64) ? 16 : 8;
+    constexpr int GB = W * C::BPW;
     const int gx = ceil_div(ps->nblk, GB);
     const int tok_chunk = pick_tok_chunk(M, gx, PS_TM);
     size_t smem = (size_t)2 * GB * PS_TM * C::LD * sizeof(__half);
-    const bool affine = ((PS_WARPS * 32) % (ps->p * (GB / 8))) == 0;
-    auto kern = affine ? pass_strided_kernel<P, true> : pass_strided_kernel<P, false>;
+    const bool affine = ((W * 32) % (ps->p * (GB / 8))) == 0;
+    auto kern = affine ? pass_strided_kernel<P, true, W> : pass_strided_kernel<P, false, W>;
     if (smem > 48 * 1024) QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(gx, ceil_div(M, tok_chunk));
-    kern<<<grid, PS_WARPS * 32, smem, s>>>(in, out, F, M, n, ps->p, ps->nblk, ps->shared, tok_chunk);
+    kern<<<grid, W * 32, smem, s>>>(in, out, F, M, n, ps->p, ps->nblk, ps->shared, tok_chunk);
     QUIP_LAUNCHED("pass_strided_kernel");
   }
   return QUIP_OK;

@@ -153,19 +153,30 @@ __device__ __forceinline__ void weight_producer_loop(int pw, int grp, int lane, 
   const int l = 4 * g + t;                       // "lane" index of the native layout
   const int NRB = N >> 4;
   uint32_t it_base = 0;                          // stages consumed by earlier tiles
+  const int rbl0 = pw, rbl1 = pw + 4;            // this thread serves row blocks pw and pw+4 of every tile
+  TcWords<BITS> c0, c1, n0, n1;
+  // the first super-block of a tile is fetched while the previous tile is still being expanded, so the
+  // ~1 us global-load latency is not exposed at every tile boundary
+  auto fetch_first = [&](int tile, TcWords<BITS>& a, TcWords<BITS>& b) {
+    const bool in_range = tile < num_tiles && grp < KSB;
+    const int rb_base = in_range ? rb_base_of(tile) : 0;
+    tc_load_words<BITS>(q + ((int64_t)(rb_base + rbl0) * KSB + grp) * sb_words(BITS), l, a, in_range && rb_base + rbl0 < NRB);
+    tc_load_words<BITS>(q + ((int64_t)(rb_base + rbl1) * KSB + grp) * sb_words(BITS), l, b, in_range && rb_base + rbl1 < NRB);
+  };
+  fetch_first(first_tile, c0, c1);
   for (int tile = first_tile; tile < num_tiles; tile += tile_step, it_base += 2u * (uint32_t)KSB) {
     const int rb_base = rb_base_of(tile);
-    const int rbl0 = pw, rbl1 = pw + 4;          // this thread serves row blocks pw and pw+4 of the tile
     const bool v0 = rb_base + rbl0 < NRB, v1 = rb_base + rbl1 < NRB;
     const uint32_t* q0 = q + (int64_t)(rb_base + rbl0) * KSB * sb_words(BITS);
     const uint32_t* q1 = q + (int64_t)(rb_base + rbl1) * KSB * sb_words(BITS);
-    TcWords<BITS> c0, c1, n0, n1;
-    tc_load_words<BITS>(q0 + (int64_t)grp * sb_words(BITS), l, c0, v0 && grp < KSB);
-    tc_load_words<BITS>(q1 + (int64_t)grp * sb_words(BITS), l, c1, v1 && grp < KSB);
     for (int ksb = grp; ksb < KSB; ksb += TC_PROD_GROUPS) {
       const bool more = ksb + TC_PROD_GROUPS < KSB;
-      tc_load_words<BITS>(q0 + (int64_t)(ksb + TC_PROD_GROUPS) * sb_words(BITS), l, n0, v0 && more);
-      tc_load_words<BITS>(q1 + (int64_t)(ksb + TC_PROD_GROUPS) * sb_words(BITS), l, n1, v1 && more);
+      if (more) {
+        tc_load_words<BITS>(q0 + (int64_t)(ksb + TC_PROD_GROUPS) * sb_words(BITS), l, n0, v0);
+        tc_load_words<BITS>(q1 + (int64_t)(ksb + TC_PROD_GROUPS) * sb_words(BITS), l, n1, v1);
+      } else {
+        fetch_first(tile + tile_step, n0, n1);
+      }
 #pragma unroll
       for (int half = 0; half < 2; ++half) {     // two 64-k stages per 128-k super-block
         const uint32_t it = it_base + 2u * (uint32_t)ksb + (uint32_t)half;

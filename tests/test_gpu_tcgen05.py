@@ -69,3 +69,19 @@ def test_big_block_pass_on_tensor_cores():
         assert ofw.rel_err(got, want) < 4e-4, (p, nblk, M)
         legacy = run_pass(X, F, p, nblk, False, impl=3)        # mma.sync tiled kernel
         assert ofw.rel_err(legacy, want) < 4e-4
+
+
+@pytest.mark.parametrize('M', [129, 192, 193, 300, 2048])
+@pytest.mark.parametrize('symmetric', [True, False])
+def test_qgemm_ts_mode_vs_oracle(M, symmetric):
+    """TS-mode kernel: expanded weights written to TMEM by tcgen05.st, MMA with A from TMEM (2-bit)."""
+    from gpu_util import run_qgemm
+    shapes = [(128, 128), (256, 1024), (384, 640), (48, 256)] if M < 2048 else [(512, 1024), (4096, 4096)]
+    for (N, K) in shapes:
+        if (N, K) == (4096, 4096) and not symmetric:
+            continue
+        codes, scales, zeros, X, bias, want = _qgemm_case(2, N, K, M, symmetric, 7 * M + N)
+        z, _ = run_qgemm(codes, scales, zeros, 2, X, path=4, bias=bias, symmetric=symmetric)
+        assert not np.isnan(z.astype(np.float32)).any()
+        err = ofw.rel_err(z, want)
+        assert err < 3e-4, (M, symmetric, N, K, err)

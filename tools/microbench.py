@@ -144,7 +144,7 @@ def main():
         res.append(bench_qgemm(11008, 4096, 2048, 2, 2, 2, peaks)); print(res[-1], flush=True)
     if 'tc2' in what:
         for (N, K) in shapes:
-            for path in (2, 3):
+            for path in (2, 3, 4):
                 res.append(bench_qgemm(N, K, 2048, 2, path, 2, peaks)); print(res[-1], flush=True)
     if 'tune' in what:
         lib = _lib.load()
@@ -158,6 +158,8 @@ def main():
             for n in (4096, 11008):
                 r = bench_gather(n, 2048); r['gather_rows'] = R; res.append(r); print(r, flush=True)
         lib.quip_config(b'gather_rows', 0)
+    if 'prof_ts' in what:
+        res.append(bench_qgemm(4096, 4096, 2048, 2, 4, 2, peaks)); print(res[-1], flush=True)
     if 'prof_tc2' in what:
         res.append(bench_qgemm(4096, 4096, 2048, 2, 3, 2, peaks)); print(res[-1], flush=True)
     if 'prof_skinny' in what:
@@ -167,6 +169,10 @@ def main():
         for (N, K) in shapes:
             for M in (1, 2048):
                 res.append(bench_dense(N, K, M, peaks)); print(res[-1], flush=True)
+    if 'pass2048' in what:
+        for (n, p, nblk, st) in [(4096, 64, 64, False), (4096, 64, 64, True), (11008, 688, 16, False), (11008, 16, 688, True)]:
+            res.append(bench_pass(n, p, nblk, st, 2048)); print(res[-1], flush=True)
+        res.append(bench_gather(4096, 2048)); print(res[-1], flush=True)
     if 'pass' in what:
         for M in (1, 2048):
             for (n, p, nblk, st) in [(4096, 64, 64, False), (4096, 64, 64, True), (11008, 688, 16, False), (11008, 16, 688, True)]:
