@@ -238,11 +238,80 @@ _workspaces = {}
 
 
 def _workspace(device, nbytes):
-    ws = _workspaces.get(device)
+    """One workspace per (device, stream): kernels of different streams may run concurrently."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _workspaces[device] = ws
+        _workspaces[key] = ws
     return ws
+
+
+class SiblingGroup:
+    """Sibling QuantLinears that consume the SAME input (q/k/v; gate/up) run concurrently on side streams.
+
+    Each packed forward is a chain of ~7 dependent kernels, several of them latency- rather than
+    bandwidth-bound, and the contraction's tile count rarely fills a whole number of waves; three independent
+    chains interleave on the SMs instead of queueing.  The first sibling called with a new input launches all
+    of them (itself on the caller's stream, the others on their own streams after an event on the input);
+    the later siblings return the already-launched result after making the caller's stream wait for it.
+    Results are bit-identical to the serial order (same kernels, per-stream workspaces)."""
+
+    def __init__(self, members):
+        self.members = list(members)
+        self.streams = None
+        self._key = None
+        self._outs = [None] * len(self.members)
+        self._events = [None] * len(self.members)
+        for i, m in enumerate(self.members):
+            m._group, m._group_index = self, i
+
+    def dissolve(self):
+        for m in self.members:
+            m._group, m._group_index = None, 0
+
+    def get(self, index, x):
+        key = (id(x), x.data_ptr(), tuple(x.shape), x._version)
+        if key != self._key or self._outs[index] is None:
+            dev = x.device
+            if self.streams is None or self.streams[0].device != dev:
+                self.streams = [torch.cuda.Stream(device=dev) for _ in self.members[1:]]
+            cur = torch.cuda.current_stream(dev)
+            ready = torch.cuda.Event()
+            ready.record(cur)
+            order = [index] + [j for j in range(len(self.members)) if j != index]
+            for slot, j in enumerate(order):
+                if slot == 0:
+                    self._outs[j] = self.members[j]._forward_impl(x)
+                    self._events[j] = None
+                    continue
+                st = self.streams[slot - 1]
+                st.wait_event(ready)
+                with torch.cuda.stream(st):
+                    y = self.members[j]._forward_impl(x)
+                    ev = torch.cuda.Event()
+                    ev.record(st)
+                x.record_stream(st)
+                self._outs[j], self._events[j] = y, ev
+            self._key = key
+        y, ev = self._outs[index], self._events[index]
+        self._outs[index] = None
+        if ev is not None:
+            cur = torch.cuda.current_stream(x.device)
+            cur.wait_event(ev)
+            y.record_stream(cur)
+        return y
+
+
+def group_siblings(model):
+    """Group q/k/v and gate/up (Llama) or q/k/v (OPT) QuantLinears of every decoder layer.  Returns the groups."""
+    groups = []
+    for mod in model.modules():
+        for names in (('q_proj', 'k_proj', 'v_proj'), ('gate_proj', 'up_proj')):
+            members = [getattr(mod, n, None) for n in names]
+            if all(isinstance(m, QuantLinear) for m in members):
+                groups.append(SiblingGroup(members))
+    return groups
 
 
 # ----------------------------------------------------------------------------------------------
@@ -287,6 +356,7 @@ class QuantLinear(nn.Module):
                 self.register_buffer(f'{side}_f0', torch.zeros((nb0, first, first), dtype=torch.float16))
                 self.register_buffer(f'{side}_f1', torch.zeros((nb1, second, second), dtype=torch.float16))
         self._desc = None
+        self._group, self._group_index = None, 0
 
     # -- construction ------------------------------------------------------------------------
     def pack(self, linear, scales, zeros):
@@ -394,6 +464,11 @@ class QuantLinear(nn.Module):
 
     # -- forward -------------------------------------------------------------------------------
     def forward(self, x):
+        if self._group is not None and x.is_cuda:
+            return self._group.get(self._group_index, x)
+        return self._forward_impl(x)
+
+    def _forward_impl(self, x):
         if x.shape[-1] != self.infeatures:
             raise ValueError(f'expected last dimension {self.infeatures}, got {tuple(x.shape)}')
         if not (x.is_cuda and self.qweight.is_cuda):

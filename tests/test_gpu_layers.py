@@ -94,3 +94,31 @@ def test_forward_is_linear_and_deterministic():
 def plan_order(tp):
     from quip_b200.incoherence import plan_side
     return plan_side(tp.U, 'U').order, plan_side(tp.V, 'V').order
+
+
+def test_sibling_group_overlap_is_bit_identical():
+    """q/k/v-style siblings launched concurrently on side streams give exactly the serial results."""
+    from quip_b200 import quant as Q
+    from quip_b200.synth import synth_layer_parts
+    mods = []
+    for i, N in enumerate((256, 128, 384)):
+        tp = synth_layer_parts(K=512, N=N, bits=2, incoh='blocked', rescale=True, bias=(i == 1), seed=20 + i)
+        ql = Q.QuantLinear(infeatures=512, outfeatures=N, **Q.spec_from_parts(tp))
+        ql.pack_parts(tp)
+        mods.append(ql.cuda())
+    g = torch.Generator(device='cuda').manual_seed(1)
+    xs = [torch.randn(M, 512, device='cuda', generator=g).half() for M in (3, 300, 64)]
+    serial = [[m(x).clone() for m in mods] for x in xs]
+    grp = Q.SiblingGroup(mods)
+    for rep in range(2):
+        for x, want in zip(xs, serial):
+            got = [m(x) for m in mods]                  # q, k, v order; k and v come from the side streams
+            torch.cuda.synchronize()
+            for a, b in zip(got, want):
+                assert torch.equal(a, b)
+            got_rev = [m(x.clone()) for m in reversed(mods)]   # a different first caller
+            torch.cuda.synchronize()
+            for a, b in zip(reversed(got_rev), want):
+                assert torch.equal(a, b)
+    grp.dissolve()
+    assert torch.equal(mods[0](xs[0]), serial[0][0])
