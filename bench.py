@@ -267,17 +267,20 @@ def main():
     value = world * a.steps * SEQ / (ms / 1e3)
     e2e_value = world * a.steps * SEQ / (e2e_ms / 1e3)
     achieved = tfl.value / (tms.value / 1e3) / 1e12 if tms.value > 0 else None
-    traffic = None
+    traffic, traffic_note = None, None
     prof = os.path.join(ROOT, 'profiles', 'ncu_qgemm_tc_latest.json')
     if os.path.exists(prof):
-        traffic = json.load(open(prof)).get('dram_bytes_per_launch')
+        pj = json.load(open(prof))
+        traffic = pj.get('dram_bytes_per_launch')
+        traffic_note = ('dram__bytes_read+write of one ncu --set full capture, %s: algorithmic %.1f MB (the activations '
+                        'stay largely L2-resident between the kernels of one linear)' % (pj.get('shape'), pj.get('algorithmic_bytes', 0) / 1e6))
     out = dict(base, value=value, ms_per_step=ms / a.steps, dtype='f16', impl='ours', gpu_launches=int(launches),
                e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=SEQ * 8, d2h_bytes_per_step=4,
                         api='quip_b200.llama.llama_eval'),
                roofline=dict(bound='tensor', kernel=('qgemm_tc2_kernel<2> (tcgen05 cta_group::2 packed GEMM)' if os.environ.get('QUIP_TC2') == '1'
                                      else 'qgemm_tc_kernel<2,256> (tcgen05 packed GEMM)'), achieved=achieved,
                              peak=pk['tflops_sustained'], unit='TFLOP/s', frac=(achieved / pk['tflops_sustained']) if achieved else None,
-                             traffic=traffic, launches_timed=int(tn.value), kernel_ms_per_step=tms.value / a.steps,
+                             traffic=traffic, traffic_note=traffic_note, launches_timed=int(tn.value), kernel_ms_per_step=tms.value / a.steps,
                              share_of_step=tms.value / serial_ms,
                              measured_in=('serial replay of the same K steps with CUDA events around every launch '
                                           '(sibling-stream overlap off, %.2f ms/step); the headline timed region runs '

@@ -130,7 +130,9 @@ def eval_ppl(model, arch: Arch, testenc, dev, sample_ids: Optional[List[int]] = 
     model.config.use_cache = False
     layers = arch.layers(model)
     if not offload:
-        model.to(dev)
+        if getattr(model, '_quip_resident_on', None) != str(dev):     # walking a 7B module tree costs milliseconds
+            model.to(dev)
+            model._quip_resident_on = str(dev)
     else:
         for mod in arch.pre(model):
             mod.to(dev)
