@@ -62,6 +62,19 @@ class _Stop(Exception):
     pass
 
 
+def _resident(model, arch, dev):
+    """Cheap check that the model already lives on `dev` (first / last decoder layer, embedding, head)."""
+    def on(mod):
+        t = next(iter(mod.parameters()), None)
+        if t is None:
+            t = next(iter(mod.buffers()), None)
+        return t is None or (t.device.type == dev.type and (dev.index is None or t.device.index == dev.index))
+    layers = arch.layers(model)
+    mods = [layers[0], layers[len(layers) - 1], arch.head(model)] + list(arch.pre(model))
+    qs = [m for m in layers[len(layers) - 1].modules() if hasattr(m, 'qweight')]
+    return all(on(m) for m in mods + qs[:1])
+
+
 class Catcher(nn.Module):
     """Stands in for decoder layer 0, records its inputs and aborts the forward (opt.py:222-241)."""
 
@@ -130,9 +143,8 @@ def eval_ppl(model, arch: Arch, testenc, dev, sample_ids: Optional[List[int]] = 
     model.config.use_cache = False
     layers = arch.layers(model)
     if not offload:
-        if getattr(model, '_quip_resident_on', None) != str(dev):     # walking a 7B module tree costs milliseconds
+        if not _resident(model, arch, torch.device(dev)):              # walking a 7B module tree costs milliseconds
             model.to(dev)
-            model._quip_resident_on = str(dev)
     else:
         for mod in arch.pre(model):
             mod.to(dev)
