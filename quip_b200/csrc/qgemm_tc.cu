@@ -27,7 +27,7 @@ struct TcCfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (200 * 1024) / STAGE_BYTES;    // 256 -> 4, 128 -> 6
   static constexpr int TMEM_COLS = 2 * BN;                     // double-buffered accumulator
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 8192 /*epilogue*/;
 };
 
 // DENSE = false: A is the packed matrix (N rows, K columns), expanded by the producer warps.
@@ -50,6 +50,7 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint64_t* tmem_full = empty + C::STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  __half* epi_stage = reinterpret_cast<__half*>(smem_gen + (size_t)C::STAGES * C::STAGE_BYTES + 256);   // 4 x 2 KB
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // packed GEMM: 128 output rows (MMA M) x BN tokens (MMA N).  DENSE pass: 128 TOKENS (MMA M) x BN factor rows
@@ -188,7 +189,8 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           if (!symmetric) Rn = sc * (0.5f * (float)((1 << BITS) - 1)) - zeros[n];
           if (bias) bn = __half2float(bias[n]);
         }
-        __half* zcol = z + n;
+        __half* stage = epi_stage + (warp - 2) * EPI_STAGE_HALVES;
+        const int n_warp = (rr % tiles_n) * TC_BM + quarter * 32;
         mbar_wait(&tmem_full[as], aph);
         tc_fence_after();
 #pragma unroll 1
@@ -196,17 +198,16 @@ qgemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           uint32_t r[32];
           tmem_ld32(taddr + (uint32_t)c0, r);
           tmem_ld_wait();
-          if (n < N) {
+          float v[32];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
+          for (int c = 0; c < 32; ++c) {
+            v[c] = Pn * __uint_as_float(r[c]) + bn;
+            if (!symmetric) {
               const int m = m0 + c0 + c;
-              if (m < M) {
-                float v = Pn * __uint_as_float(r[c]) + bn;
-                if (!symmetric) v += Rn * __ldg(&xsum[m]);
-                zcol[(int64_t)m * ldz] = __float2half_rn(v);
-              }
+              v[c] += Rn * (m < M ? __ldg(&xsum[m]) : 0.f);
             }
           }
+          epilogue_store_chunk(stage, v, z, ldz, m0 + c0, M, n_warp, N, lane);
         }
       }
       tc_fence_before();

@@ -26,7 +26,7 @@ struct T2Cfg {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = 6;
   static constexpr int TMEM_COLS = 512;                // two 256-column accumulators
-  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 + 256 + 8192;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -84,6 +84,7 @@ qgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __r
   uint64_t* tmem_full = empty + C::STAGES;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]       (used in the leader)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  __half* epi_stage = reinterpret_cast<__half*>(smem_gen + (size_t)C::STAGES * C::STAGE_BYTES + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -186,22 +187,23 @@ qgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __r
       mbar_wait(&tmem_full[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * C::BN);
+      __half* stage = epi_stage + (warp - 2) * EPI_STAGE_HALVES;
+      const int n_warp = n - lane;
 #pragma unroll 1
       for (int c0 = 0; c0 < C::BN; c0 += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + (uint32_t)c0, r);
         tmem_ld_wait();
-        if (n < N) {
+        float v[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < 32; ++c) {
+          v[c] = Pn * __uint_as_float(r[c]) + bn;
+          if (!symmetric) {
             const int m = m0 + c0 + c;
-            if (m < M) {
-              float v = Pn * __uint_as_float(r[c]) + bn;
-              if (!symmetric) v += Rn * __ldg(&xsum[m]);
-              z[(int64_t)m * N + n] = __float2half_rn(v);
-            }
+            v[c] += Rn * (m < M ? __ldg(&xsum[m]) : 0.f);
           }
         }
+        epilogue_store_chunk(stage, v, z, N, m0 + c0, M, n_warp, N, lane);
       }
       tc_fence_before();
       __syncwarp();

@@ -139,6 +139,28 @@ __device__ __forceinline__ void tc_store_chunk(const TcWords<BITS>& r, uint32_t 
 }
 
 
+// Epilogue store of one 32-token chunk of a warp's 32 output rows.  After tcgen05.ld every lane owns ONE
+// output row and 32 consecutive tokens, i.e. addresses N*2 bytes apart: storing them directly is 32
+// two-byte warp stores per chunk (measured ~30 cycles each; ~16 us per 128x256 tile, which left the last
+// tile's epilogue fully exposed).  Transposing the chunk through a 2 KB warp-private shared-memory patch
+// turns it into 4 x 16-byte stores per lane, 64 contiguous bytes per token row.
+constexpr int EPI_STAGE_HALVES = 32 * 32;      // per epilogue warp
+__device__ __forceinline__ void epilogue_store_chunk(__half* stage, const float (&v)[32], __half* __restrict__ z,
+                                                     int64_t ldz, int m_base, int M, int n_base, int N, int lane) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) stage[c * 32 + lane] = __float2half_rn(v[c]);
+  __syncwarp();
+  const int seg = (lane & 3) * 8;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int t = (lane >> 2) + 8 * r;
+    const uint4 val = *reinterpret_cast<const uint4*>(&stage[t * 32 + seg]);
+    const int m = m_base + t, n = n_base + seg;
+    if (m < M && n < N) *reinterpret_cast<uint4*>(z + (int64_t)m * ldz + n) = val;
+  }
+  __syncwarp();
+}
+
 // Weight-producer loop shared by the 1-CTA and 2-CTA kernels.  Group `grp` (4 warps) expands the k
 // super-blocks grp, grp+G, ... of every tile into stages 2*ksb and 2*ksb+1 of the global stage sequence.
 // Two groups are needed because fence.proxy.async compiles to MEMBAR.ALL.CTA, which also waits for the
