@@ -18,7 +18,7 @@
 namespace quip {
 
 int g_gather_rows = 0;        // quip_config("gather_rows", R)
-int g_pass_min_tiles = 2;     // quip_config("pass_min_tiles", t): token tiles per CTA in the small-block passes
+int g_pass_min_tiles = 4;     // quip_config("pass_min_tiles", t): token tiles per CTA in the small-block passes
 
 // ----------------------------------------------------------------------------------------------
 // R rows per CTA share one read of the index vector (4 bytes/feature, twice the fp16 row itself)

@@ -96,10 +96,6 @@ pass_contig_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
   const int64_t m_end = m_begin + tok_chunk < M ? m_begin + tok_chunk : M;
   const int ntiles = (int)((m_end - m_begin + C::TM - 1) / C::TM);
 
-  uint32_t bf[C::BPW][C::KS][C::NT][2];
-#pragma unroll
-  for (int bb = 0; bb < C::BPW; ++bb)
-    load_bfrags<P>(F + (int64_t)(shared ? 0 : min(blk0 + bb, nblk - 1)) * p * p, p, blk0 + bb < nblk, g, t, bf[bb]);
   if (P != p) {                                                 // zero the padding columns once
     const int padw = P - p;
     for (int c = lane; c < PC_STAGES * C::BPW * C::TM * padw; c += 32)
@@ -152,6 +148,10 @@ pass_contig_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
     if (s < ntiles) issue(s);
     asm volatile("cp.async.commit_group;");
   }
+  uint32_t bf[C::BPW][C::KS][C::NT][2];                         // factors fetched while the first tiles are in flight
+#pragma unroll
+  for (int bb = 0; bb < C::BPW; ++bb)
+    load_bfrags<P>(F + (int64_t)(shared ? 0 : min(blk0 + bb, nblk - 1)) * p * p, p, blk0 + bb < nblk, g, t, bf[bb]);
   for (int it = 0; it < ntiles; ++it) {
     asm volatile("cp.async.wait_group %0;" ::"n"(PC_STAGES - 2));
     __syncwarp();
@@ -187,7 +187,9 @@ pass_strided_kernel(const __half* __restrict__ in, __half* __restrict__ out, con
   constexpr int GB = W * C::BPW;                         // blocks per CTA
   constexpr int CG = GB / 8;                                    // 16-byte chunks per (tok, j)
   constexpr int TILE = GB * PS_TM * C::LD;                      // halves per buffer
-  constexpr int NCH = (PS_TM * P * CG + W * 32 - 1) / (W * 32);
+  // a "chunk" is two adjacent elements j, j+1 of 8 adjacent blocks for one token: two 16-byte global runs,
+  // transposed with 32-bit shared-memory accesses (sub-word st/ld.shared are several times slower)
+  constexpr int NCH = (PS_TM * (P / 2) * CG + W * 32 - 1) / (W * 32);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __half* T = reinterpret_cast<__half*>(smem_raw);              // [2][GB][TM][LD]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
@@ -195,39 +197,34 @@ pass_strided_kernel(const __half* __restrict__ in, __half* __restrict__ out, con
   const int64_t m_begin = (int64_t)blockIdx.y * tok_chunk;
   const int64_t m_end = m_begin + tok_chunk < M ? m_begin + tok_chunk : M;
   const int ntiles = (int)((m_end - m_begin + PS_TM - 1) / PS_TM);
-  const int nchunks = PS_TM * p * CG;
+  const int hp = p / 2;                                         // p is even (p % 8 == 0)
+  const int nchunks = PS_TM * hp * CG;
 
-  uint32_t bf[C::BPW][C::KS][C::NT][2];
-#pragma unroll
-  for (int bb = 0; bb < C::BPW; ++bb) {
-    const int blk = b0 + warp * C::BPW + bb;
-    load_bfrags<P>(F + (int64_t)(shared ? 0 : min(blk, nblk - 1)) * p * p, p, blk < nblk, g, t, bf[bb]);
-  }
   if (P != p) {
     const int padw = P - p;
     for (int c = tid; c < 2 * GB * PS_TM * padw; c += W * 32)
       T[(c / padw) * C::LD + p + c % padw] = __float2half(0.f);
   }
 
-  // per-thread chunk map (tile-invariant).  With 256 % (p*CG) == 0 it is affine in r (token += 256/(p*CG), same
-  // (j, block run)); other block sizes take the generic path with divisions.
-  const int ppc = p * CG;
-  constexpr bool affine = AFFINE;                             // host guarantees 256 % (p*CG) == 0
+  // per-thread chunk map (tile-invariant).  With (32 W) % (hp*CG) == 0 it is affine in r (token += 32W/(hp*CG),
+  // same (j pair, block run)); other block sizes take the generic path with divisions.
+  const int ppc = hp * CG;
+  constexpr bool affine = AFFINE;
   const int tstep = affine ? (W * 32) / ppc : 0;
   auto chunk = [&](int r, int& soff, int& goff, int& tok) -> bool {
-    int c8, j;
+    int c8, jp;
     if (affine) {
-      tok = tid / ppc + r * tstep; c8 = tid % CG; j = (tid / CG) % p;
+      tok = tid / ppc + r * tstep; c8 = tid % CG; jp = (tid / CG) % hp;
     } else {
       const int c = tid + r * W * 32;
       if (c >= nchunks) return false;
-      c8 = c % CG; j = (c / CG) % p; tok = c / ppc;
+      c8 = c % CG; jp = (c / CG) % hp; tok = c / ppc;
     }
     if (tok >= PS_TM) return false;
     const int blk = b0 + c8 * 8;
     if (blk >= nblk) return false;
-    soff = ((c8 * 8) * PS_TM + tok) * C::LD + j;
-    goff = tok * n + j * nblk + blk;
+    soff = ((c8 * 8) * PS_TM + tok) * C::LD + 2 * jp;            // even -> 4-byte aligned
+    goff = tok * n + (2 * jp) * nblk + blk;
     return true;
   };
   int s0 = 0, g0 = 0, t0 = 0;
@@ -239,28 +236,42 @@ pass_strided_kernel(const __half* __restrict__ in, __half* __restrict__ out, con
   else ok = chunk(r, so, go, tk);
   constexpr int BSTRIDE = PS_TM * C::LD;                        // smem distance between adjacent blocks' tiles
 
-  uint4 pre[NCH];
+  uint4 pre[NCH][2];                                            // rows j and j+1 of each chunk
   auto prefetch = [&](int tile) {
     const int64_t m0 = m_begin + (int64_t)tile * PS_TM;
     const __half* src0 = in + m0 * n;
 #pragma unroll
     for (int r = 0; r < NCH; ++r) {
-      pre[r] = make_uint4(0, 0, 0, 0);
+      pre[r][0] = pre[r][1] = make_uint4(0, 0, 0, 0);
       QUIP_CHUNK(r, so, go, tk, ok)
-      if (ok && m0 + tk < m_end) pre[r] = ldg_nc_v4(src0 + go);
+      if (ok && m0 + tk < m_end) {
+        pre[r][0] = ldg_nc_v4(src0 + go);
+        pre[r][1] = ldg_nc_v4(src0 + go + nblk);
+      }
     }
   };
 
-  prefetch(0);
+  prefetch(0);                                                  // first tile in flight while the factors are fetched
+  uint32_t bf[C::BPW][C::KS][C::NT][2];
+#pragma unroll
+  for (int bb = 0; bb < C::BPW; ++bb) {
+    const int blk = b0 + warp * C::BPW + bb;
+    load_bfrags<P>(F + (int64_t)(shared ? 0 : min(blk, nblk - 1)) * p * p, p, blk < nblk, g, t, bf[bb]);
+  }
   for (int it = 0; it < ntiles; ++it) {
     __half* buf = T + (size_t)(it & 1) * TILE;
 #pragma unroll
     for (int r = 0; r < NCH; ++r) {
       QUIP_CHUNK(r, so, go, tk, ok)
       if (ok) {
-        const __half* h = reinterpret_cast<const __half*>(&pre[r]);
+        const uint32_t* lo = reinterpret_cast<const uint32_t*>(&pre[r][0]);   // element j   of blocks 0..7
+        const uint32_t* hi = reinterpret_cast<const uint32_t*>(&pre[r][1]);   // element j+1 of blocks 0..7
 #pragma unroll
-        for (int i = 0; i < 8; ++i) buf[so + i * BSTRIDE] = h[i];
+        for (int w = 0; w < 4; ++w) {
+          // blocks 2w and 2w+1: pack (j, j+1) of one block into a word
+          *reinterpret_cast<uint32_t*>(&buf[so + (2 * w) * BSTRIDE]) = __byte_perm(lo[w], hi[w], 0x5410);
+          *reinterpret_cast<uint32_t*>(&buf[so + (2 * w + 1) * BSTRIDE]) = __byte_perm(lo[w], hi[w], 0x7632);
+        }
       }
     }
     __syncthreads();
@@ -275,10 +286,16 @@ pass_strided_kernel(const __half* __restrict__ in, __half* __restrict__ out, con
     for (int r = 0; r < NCH; ++r) {
       QUIP_CHUNK(r, so, go, tk, ok)
       if (ok && m0 + tk < m_end) {
-        __align__(16) __half h[8];
+        uint32_t lo[4], hi[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) h[i] = buf[so + i * BSTRIDE];
-        *reinterpret_cast<uint4*>(dst0 + go) = *reinterpret_cast<const uint4*>(h);
+        for (int w = 0; w < 4; ++w) {
+          const uint32_t e = *reinterpret_cast<const uint32_t*>(&buf[so + (2 * w) * BSTRIDE]);      // block 2w  : (i, i+1)
+          const uint32_t o = *reinterpret_cast<const uint32_t*>(&buf[so + (2 * w + 1) * BSTRIDE]);  // block 2w+1: (i, i+1)
+          lo[w] = __byte_perm(e, o, 0x5410);      // row i  : blocks 2w, 2w+1
+          hi[w] = __byte_perm(e, o, 0x7632);      // row i+1: blocks 2w, 2w+1
+        }
+        *reinterpret_cast<uint4*>(dst0 + go) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        *reinterpret_cast<uint4*>(dst0 + go + nblk) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
       }
     }
   }
@@ -318,7 +335,7 @@ static int launch_fast(const QuipPass* ps, const __half* in, __half* out, int64_
     const int gx = ceil_div(ps->nblk, GB);
     const int tok_chunk = pick_tok_chunk(M, gx, PS_TM);
     size_t smem = (size_t)2 * GB * PS_TM * C::LD * sizeof(__half);
-    const bool affine = ((W * 32) % (ps->p * (GB / 8))) == 0;
+    const bool affine = ((W * 32) % ((ps->p / 2) * (GB / 8))) == 0;
     auto kern = affine ? pass_strided_kernel<P, true, W> : pass_strided_kernel<P, false, W>;
     if (smem > 48 * 1024) QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(gx, ceil_div(M, tok_chunk));

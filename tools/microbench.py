@@ -148,7 +148,7 @@ def main():
                 res.append(bench_qgemm(N, K, 2048, 2, path, 2, peaks)); print(res[-1], flush=True)
     if 'tune' in what:
         lib = _lib.load()
-        for mt in (1, 2, 4, 8):
+        for mt in (1, 2, 4):
             lib.quip_config(b'pass_min_tiles', mt)
             for (n, p, nblk, st) in [(4096, 64, 64, False), (4096, 64, 64, True), (11008, 16, 688, True)]:
                 r = bench_pass(n, p, nblk, st, 2048); r['pass_min_tiles'] = mt; res.append(r); print(r, flush=True)
