@@ -15,12 +15,17 @@ Native layout (what the sm_100a kernels read; documented in DESIGN.md):
   [row_block][k_superblock].  Inside a super-block the data are laid out per
   *lane* l = 4*g + t of a warp, lane l owning rows {g, g+8} and, in each of the
   4 chunks of 32 k, the 8 consecutive k = 32*ch + 8*t + [0,8).  Those 16 codes
-  per (lane, chunk) are stored as 8 "pairs" j = 2*(pos//2) + (row >= 8), the
+  per (lane, chunk) are stored as 8 "pairs" (two consecutive k of one row), the
   first element of a pair in the low half-word and the second in the high one,
-  so that one shift + one LOP3 drops both into the mantissa of an fp16 pair:
+  so that one shift + one LOP3 drops both into the mantissa of an fp16 pair.
+  Pair u = pos//2 of row half r = (row >= 8) sits in slot j = 2*perm(u) + r,
+  perm = [0,2,1,3]: then byte b of the word holds k offsets {0,2,1,3}[b] (low
+  nibble) and 4+{0,2,1,3}[b] (high nibble), each nibble = (row g, row g+8), which
+  is what the int8 tensor-core path masks out with four ANDs (csrc/common.cuh):
       bits=2: 1 word / (lane,chunk): pair j at bits 2j and 16+2j;
               lane's 4 chunk words are contiguous (one 128-bit load).
-      bits=4: 2 words / (lane,chunk) (pos 0-3, pos 4-7): pair j' at bits 4j', 16+4j';
+      bits=4: 2 words / (lane,chunk) (pos 0-3, pos 4-7): slot j' = 2*((pos%4)//2) + (row >= 8)
+              at bits 4j', 16+4j';
               two 128-bit segments per super-block (chunks 0-1, chunks 2-3).
       bits=3: the upper two bits use the bits=2 layout ("hi plane"), followed by a
               "lo plane" of the lowest bit: 2 words / lane, word ch//2, pair
@@ -137,7 +142,8 @@ def native_index(N, K, bits):
     """For every (n, k): list of (word index, bit shift, code-bit shift, nbits) planes."""
     sb, lane, ch, pos, hi_row, e = _coords(N, K)
     base = sb * SB_WORDS[bits]
-    j = 2 * (pos // 2) + hi_row                       # pair 0..7 inside a (lane, chunk)
+    u = pos // 2
+    j = 2 * ((u % 2) * 2 + u // 2) + hi_row           # pair slot 0..7 inside a (lane, chunk), see below
     if bits == 2:
         return [(base + lane * 4 + ch, 2 * j + 16 * e, 0, 2)]
     if bits == 4:

@@ -28,6 +28,8 @@ int qgemm_skinny(const QuipLinearDesc* d, const __half* x, const __half* bias, _
                  float* part, int* counters, cudaStream_t s);
 int skinny_pick_ksplit(int N, int K, int rows_per_cta);
 size_t skinny_workspace_bytes(int N, int M, int ksplit);
+int qgemv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M, cudaStream_t s);
+bool qgemv_fits(int K, int M);
 int qgemm_tc(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
              cudaStream_t s);
 int qgemm_tc2(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
@@ -36,10 +38,12 @@ int qgemm_ts(const QuipLinearDesc* d, const __half* x, const float* xsum, const 
              cudaStream_t s);
 
 extern int g_gather_rows, g_pass_min_tiles;   // rot.cu
+extern int g_gv_rbc, g_gv_persist, g_gv_int;  // qgemv.cu
 
 // tuning knobs (quip_config)
 static int g_use_tc2 = 0;        // route big-M contractions to the 2-CTA kernel
 static int g_use_ts = 0;         // route 2-bit big-M contractions to the TS-mode (A in TMEM) kernel
+static int g_use_gemv = 1;       // few-token contractions: whole-K qgemv kernel (0: the split-K kernel)
 
 constexpr size_t WS_HEADER = 16 * 1024;     // split-K arrival counters; must be zero on first use, left zero
 constexpr int SKINNY_MAX_M = 32;
@@ -125,6 +129,10 @@ static int run_qgemm_untimed(const QuipLinearDesc* d, const __half* x2, const fl
     // the skinny kernel takes <= 32 tokens per launch and sums x itself
     for (int64_t m0 = 0; m0 < M; m0 += SKINNY_MAX_M) {
       int mc = (int)((M - m0) < SKINNY_MAX_M ? (M - m0) : SKINNY_MAX_M);
+      if (g_use_gemv && qgemv_fits(d->K, mc)) {
+        if (int e = qgemv(d, x2 + m0 * d->K, bias, z + m0 * d->N, mc, s)) return e;
+        continue;
+      }
       int ksplit = M <= SKINNY_MAX_M ? skinny_pick_ksplit(d->N, d->K, 64) : 1;
       if (int e = qgemm_skinny(d, x2 + m0 * d->K, bias, z + m0 * d->N, mc, ksplit,
                                reinterpret_cast<float*>(ws + p.part), reinterpret_cast<int*>(ws), s))
@@ -151,6 +159,10 @@ extern "C" int quip_config(const char* key, int value) {
   QUIP_CHECK_ARG(key != nullptr, "null key");
   if (!strcmp(key, "tc2")) { g_use_tc2 = value; return QUIP_OK; }
   if (!strcmp(key, "ts")) { g_use_ts = value; return QUIP_OK; }
+  if (!strcmp(key, "gemv")) { g_use_gemv = value; return QUIP_OK; }
+  if (!strcmp(key, "gv_rbc")) { g_gv_rbc = value; return QUIP_OK; }
+  if (!strcmp(key, "gv_int")) { g_gv_int = value; return QUIP_OK; }
+  if (!strcmp(key, "gv_persist")) { g_gv_persist = value; return QUIP_OK; }
   if (!strcmp(key, "gather_rows")) { g_gather_rows = value; return QUIP_OK; }
   if (!strcmp(key, "pass_min_tiles")) { g_pass_min_tiles = value > 0 ? value : 1; return QUIP_OK; }
   set_error("quip_config: unknown key '%s'", key);

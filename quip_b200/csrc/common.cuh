@@ -125,23 +125,36 @@ __device__ __forceinline__ uint32_t dq3(uint32_t whi, uint32_t wlo) {
   return hadd2_u32(v, Dq<3>::kNegCenter);
 }
 
-// Expand one (lane, chunk): 16 codes -> 8 fp16x2 registers h[j], pair j = 2*(pos/2) + (row>=8).
+// Bit layout of one (lane, chunk) word group: 16 codes = rows {g, g+8} x the lane's 8 consecutive k.
+// Three consumers read the same bits, each with the cheapest extraction its datapath allows:
+//   * IMMA.16832 (qgemv.cu, 1-5 tokens): the four A registers are  w & 0x03030303, w & 0x0C0C0C0C,
+//     (w>>4) & 0x03030303, (w>>4) & 0x0C0C0C0C  -- byte j of the word holds "slot" j (bits 0-1 row g,
+//     2-3 row g+8) and slot 4+j (bits 4-5, 6-7);
+//   * HMMA.16816 / tcgen05 (fp16): a register is a pair of codes of one row at the same offset of the low
+//     and high half-word -- slots (j, j+2) -- so slot s stands for k offset {0,2,1,3,4,6,5,7}[s] and every
+//     fp16x2 register holds two consecutive k.
+// In half-word terms: pair (u = pos/2, row half r) sits at bit 2*slot2(u,r) of each half.  4-bit: word
+// pos/4, nibble slot4(u%2, r) of each half (byte j: low nibble row g, high nibble row g+8).
+__host__ __device__ constexpr int slot2(int u, int r) { return 2 * ((u & 1) * 2 + (u >> 1)) + r; }
+__host__ __device__ constexpr int slot4(int uw, int r) { return 2 * uw + r; }
+
+// Expand one (lane, chunk): 16 codes -> 8 fp16x2 registers h[2u + r] (k pair u, row half r).
 // MMA step s (k positions 4s..4s+3) uses a0..a3 = h[4s..4s+3].
 // words: bits=2 -> w[0]; bits=4 -> w[0] (pos 0-3), w[1] (pos 4-7); bits=3 -> w[0] hi, w[1] lo with LOSEL
 template <int BITS, int LOSEL = 0>
 __device__ __forceinline__ void expand_chunk(uint32_t w0, uint32_t w1, uint32_t (&h)[8]) {
   if constexpr (BITS == 2) {
-    h[0] = dq2<0>(w0); h[1] = dq2<1>(w0); h[2] = dq2<2>(w0); h[3] = dq2<3>(w0);
-    h[4] = dq2<4>(w0); h[5] = dq2<5>(w0); h[6] = dq2<6>(w0); h[7] = dq2<7>(w0);
+    h[0] = dq2<slot2(0, 0)>(w0); h[1] = dq2<slot2(0, 1)>(w0); h[2] = dq2<slot2(1, 0)>(w0); h[3] = dq2<slot2(1, 1)>(w0);
+    h[4] = dq2<slot2(2, 0)>(w0); h[5] = dq2<slot2(2, 1)>(w0); h[6] = dq2<slot2(3, 0)>(w0); h[7] = dq2<slot2(3, 1)>(w0);
   } else if constexpr (BITS == 4) {
-    h[0] = dq4<0>(w0); h[1] = dq4<1>(w0); h[2] = dq4<2>(w0); h[3] = dq4<3>(w0);
-    h[4] = dq4<0>(w1); h[5] = dq4<1>(w1); h[6] = dq4<2>(w1); h[7] = dq4<3>(w1);
+    h[0] = dq4<slot4(0, 0)>(w0); h[1] = dq4<slot4(0, 1)>(w0); h[2] = dq4<slot4(1, 0)>(w0); h[3] = dq4<slot4(1, 1)>(w0);
+    h[4] = dq4<slot4(0, 0)>(w1); h[5] = dq4<slot4(0, 1)>(w1); h[6] = dq4<slot4(1, 0)>(w1); h[7] = dq4<slot4(1, 1)>(w1);
   } else {
     constexpr int B = 8 * LOSEL;
-    h[0] = dq3<0, B + 0>(w0, w1); h[1] = dq3<1, B + 1>(w0, w1);
-    h[2] = dq3<2, B + 2>(w0, w1); h[3] = dq3<3, B + 3>(w0, w1);
-    h[4] = dq3<4, B + 4>(w0, w1); h[5] = dq3<5, B + 5>(w0, w1);
-    h[6] = dq3<6, B + 6>(w0, w1); h[7] = dq3<7, B + 7>(w0, w1);
+    h[0] = dq3<slot2(0, 0), B + slot2(0, 0)>(w0, w1); h[1] = dq3<slot2(0, 1), B + slot2(0, 1)>(w0, w1);
+    h[2] = dq3<slot2(1, 0), B + slot2(1, 0)>(w0, w1); h[3] = dq3<slot2(1, 1), B + slot2(1, 1)>(w0, w1);
+    h[4] = dq3<slot2(2, 0), B + slot2(2, 0)>(w0, w1); h[5] = dq3<slot2(2, 1), B + slot2(2, 1)>(w0, w1);
+    h[6] = dq3<slot2(3, 0), B + slot2(3, 0)>(w0, w1); h[7] = dq3<slot2(3, 1), B + slot2(3, 1)>(w0, w1);
   }
 }
 

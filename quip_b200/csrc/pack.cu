@@ -32,17 +32,17 @@ __device__ __forceinline__ void locate(const Coord& c, int64_t& word, int& shift
   int64_t base = c.sb * sb_words(BITS);
   if (BITS == 4) {
     int w = c.pos >> 2;
-    int jp = 2 * ((c.pos & 3) >> 1) + c.hi_row;
+    int jp = slot4((c.pos & 3) >> 1, c.hi_row);
     word = base + (c.ch >> 1) * 128 + c.lane * 4 + (c.ch & 1) * 2 + w;
     shift = 4 * jp + 16 * e;
   } else {
-    int j = 2 * (c.pos >> 1) + c.hi_row;
+    int j = slot2(c.pos >> 1, c.hi_row);
     word = base + c.lane * 4 + c.ch;
     shift = 2 * j + 16 * e;
   }
 }
 __device__ __forceinline__ void locate_lo3(const Coord& c, int64_t& word, int& shift) {
-  int j = 2 * (c.pos >> 1) + c.hi_row;
+  int j = slot2(c.pos >> 1, c.hi_row);
   word = c.sb * sb_words(3) + 128 + c.lane * 2 + (c.ch >> 1);
   shift = 8 * (c.ch & 1) + j + 16 * (c.pos & 1);
 }
@@ -80,7 +80,7 @@ __global__ void pack_kernel(const uint8_t* __restrict__ codes, int N, int K, uin
     for (int pos = 0; pos < 8; ++pos)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        int j = 2 * (pos >> 1) + h;
+        int j = slot2(pos >> 1, h);
         uint32_t code = c[h][pos] & cm;
         uint32_t top = BITS == 3 ? (code >> 1) : code;
         w |= top << (2 * j + 16 * (pos & 1));
@@ -98,7 +98,7 @@ __global__ void pack_kernel(const uint8_t* __restrict__ codes, int N, int K, uin
     for (int pos = 0; pos < 8; ++pos)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        int jp = 2 * ((pos & 3) >> 1) + h;
+        int jp = slot4((pos & 3) >> 1, h);
         w[pos >> 2] |= (c[h][pos] & cm) << (4 * jp + 16 * (pos & 1));
       }
     int64_t wi = base + (ch >> 1) * 128 + lane * 4 + (ch & 1) * 2;

@@ -214,11 +214,11 @@ qgemm_ts_kernel(const __grid_constant__ CUtensorMap tmap_x, const uint32_t* __re
             for (int t = 0; t < 4; ++t) {
               const uint32_t xa = __shfl_sync(0xffffffffu, wa[2 * half + cl], 4 * g + t);
               const uint32_t xb = __shfl_sync(0xffffffffu, wb[2 * half + cl], 4 * g + t);
-              const uint32_t w = (use_b ? xb : xa) >> (2 * hi);      // this row's pairs now sit at j = 0,2,4,6
-              regs[cl * 16 + t * 4 + 0] = dq2<0>(w);
-              regs[cl * 16 + t * 4 + 1] = dq2<2>(w);
-              regs[cl * 16 + t * 4 + 2] = dq2<4>(w);
-              regs[cl * 16 + t * 4 + 3] = dq2<6>(w);
+              const uint32_t w = (use_b ? xb : xa) >> (2 * hi);      // this row's pairs now sit at even slots
+              regs[cl * 16 + t * 4 + 0] = dq2<slot2(0, 0)>(w);
+              regs[cl * 16 + t * 4 + 1] = dq2<slot2(1, 0)>(w);
+              regs[cl * 16 + t * 4 + 2] = dq2<slot2(2, 0)>(w);
+              regs[cl * 16 + t * 4 + 3] = dq2<slot2(3, 0)>(w);
             }
           if (!(use_b ? vb : va)) {
 #pragma unroll

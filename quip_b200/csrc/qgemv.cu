@@ -1,0 +1,666 @@
+// Packed-integer x fp16 contraction for a handful of tokens (decode, M <= 8): the HBM-bound regime
+// of the path (reference Quant3Linear.forward is M == 1 only, quant.py:222-233, on the absent
+// quant_cuda.vecquant3matmul).  Speed of light is one pass over the packed words at ~6.5 TB/s, i.e. an
+// SM has ~22 cycles per 512-byte super-block: the limits are (1) instructions per weight on the ALU
+// pipe (LOP3/SHF retire one warp-instruction per 2 cycles per SM sub-partition) and on the legacy tensor
+// pipe (every mma.sync shape retires one per 8 cycles per sub-partition -- tools/mma_rate.cu), and
+// (2) dependent round trips to memory.  Two datapaths share one skeleton:
+//
+// * qgemv_i8_kernel (2-/4-bit, up to 5 tokens): integer tensor cores, IMMA.16832.  The codes are used as
+//   they are -- four ANDs turn one packed word into the four A registers (common.cuh) -- and a token is
+//   split once per CTA into three balanced signed bytes of round(x 2^22/amax), three B columns.  Sums of
+//   products are exact in int32; 5 ALU instructions and 1-2 MMAs per 16 weights x 32 lanes.
+//       y[m][n] = scales_n s_m (65536 I_hi + 256 I_mid + I_lo) - zeros_n S_m + bias_n,  s_m = amax_m / 2^22.
+//
+// * qgemv_kernel (fp16, HMMA.16816; 6-8 tokens and 3-bit).  The usual "mask, OR exponent, subtract" costs
+//   1.4 instructions per weight; here the subtraction is dropped: a pair of codes is masked in place
+//   inside the fp16 mantissa wherever one shift per row leaves it, which reads as 1 + c/4^(e+1) with
+//   e in {0,2} depending on the bit offset.  The token operand of that k position is pre-scaled by 4^(e-2)
+//   once per CTA when the activations are staged, so every product is 4^(e-2) x_k + c_k x_k / 64 and
+//       sum_k A_k B_k = T_m + (1/64) sum_k c_k x_k,      T_m = sum_k 4^(e(k)-2) x_k  (per token),
+//   exact in the fp32 accumulator (the offset costs at most 6 of its 24 bits).  4 shifts (two of them IMADs on
+//   the FMA pipe) + 8 LOP3 per 16 weights.  4-bit likewise; 3-bit keeps the recentring expansion.
+//   T_m and the plain row sum S_m fall out of one extra MMA per k-step against a constant A fragment
+//   (rows 0-7 ones, rows 8-15 4^(2-e)) during a CTA's first row tile.
+//       y[m][n] = scales_n (A1 (acc - T_m) + A2 S_m) - zeros_n S_m + bias_n,
+//       (A1, A2) = (64, 0) / (8, 3.5) / (256, 0) for 2 / 3 / 4 bits.
+//
+// Skeleton.  A CTA owns RBC row blocks over the *whole* K (8 warps split the k super-blocks), so the only
+// reduction is through shared memory (one barrier per tile, double-buffered): no split-K partials,
+// counters or fences.  The packed words of the first D steps are requested before anything else (they do
+// not depend on the previous kernel: with programmatic dependent launch they are in flight while it
+// drains), then the tokens are staged, then a D-deep register ring keeps D x RBC x 512 B per warp in flight.
+#include "common.cuh"
+
+namespace quip {
+
+constexpr int GV_WARPS = 8;
+constexpr int GV_XPAD = 32;            // halves; makes the 8-lane LDS.128 phases conflict-free
+
+int g_gv_rbc = 0;                      // quip_config("gv_rbc", r): row blocks per CTA tile (0 = heuristic)
+int g_gv_int = 1;                      // quip_config("gv_int", 0): fp16 tensor path for every token count
+int g_gv_persist = 1;                  // quip_config("gv_persist", 0): one CTA per row tile instead of a persistent grid
+
+template <int BITS>
+struct Gv {
+  static constexpr int kWords = BITS == 2 ? 4 : (BITS == 3 ? 6 : 8);
+  static constexpr bool kRaw = BITS != 3;                       // offset-free expansion + prescaled tokens
+  static constexpr float kA1 = BITS == 2 ? 64.f : (BITS == 3 ? 8.f : 256.f);
+  static constexpr float kA2 = BITS == 3 ? 3.5f : 0.f;
+};
+
+// fp16x2 constants
+constexpr uint32_t H2_ONE = 0x3C003C00u, H2_SIXTEENTH = 0x2C002C00u, H2_SIXTEEN = 0x4C004C00u;
+
+// token scale 4^(e-2) of k pair u (pos 2u, 2u+1 of a lane's 8 k) and its inverse
+template <int BITS>
+__device__ __forceinline__ constexpr uint32_t gv_scale(int u) {
+  if (BITS == 2) return u < 2 ? H2_ONE : H2_SIXTEENTH;
+  if (BITS == 4) return (u & 1) ? H2_SIXTEENTH : H2_ONE;
+  return H2_ONE;
+}
+template <int BITS>
+__device__ __forceinline__ constexpr uint32_t gv_inv_scale(int u) {
+  if (BITS == 2) return u < 2 ? H2_ONE : H2_SIXTEEN;
+  if (BITS == 4) return (u & 1) ? H2_SIXTEEN : H2_ONE;
+  return H2_ONE;
+}
+
+// (a & mask) | c in ONE LOP3: c must live in a register (a LOP3 encodes a single immediate), which the
+// compiler will not do on its own for a constant -- it emits an AND and an OR, doubling the ALU work.
+__device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t mask, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(mask), "r"(c));
+  return d;
+}
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) {   // a constant the optimiser cannot see through
+  uint32_t d;
+  asm("mov.b32 %0, %1;" : "=r"(d) : "r"(v));
+  return d;
+}
+
+__device__ __forceinline__ uint32_t hmul2_u32(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+
+template <int BITS>
+struct GvRegs {
+  uint32_t w[Gv<BITS>::kWords];
+};
+
+template <int BITS>
+__device__ __forceinline__ void gv_load(const uint32_t* __restrict__ base, int lane, GvRegs<BITS>& r) {
+  if constexpr (BITS == 2) {
+    uint4 v = ldg_nc_v4(base + lane * 4);
+    r.w[0] = v.x; r.w[1] = v.y; r.w[2] = v.z; r.w[3] = v.w;
+  } else if constexpr (BITS == 4) {
+    uint4 a = ldg_nc_v4(base + lane * 4), b = ldg_nc_v4(base + 128 + lane * 4);
+    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+    r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  } else {
+    uint4 a = ldg_nc_v4(base + lane * 4);
+    uint2 b = ldg_nc_v2(base + 128 + lane * 2);
+    r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+    r.w[4] = b.x; r.w[5] = b.y;
+  }
+}
+
+// chunk CH of a lane -> h[2u + r] (k pair u, row half r).  2-/4-bit: 1 + c/2^BITS/4^e, no recentring.
+// 2-bit half-word (slot2): row g pairs at bits 0 (u0), 4 (u2), 8 (u1), 12 (u3), row g+8 two bits higher.
+// w<<4 / w<<2 put u0 on mantissa bit 4 (e = 2) and u2 on bit 8 (e = 0) for the two rows, w>>4 / w>>6 do the
+// same for u1 / u3.  Bits that cross the half-word boundary land outside every mask.
+template <int BITS, int CH>
+__device__ __forceinline__ void gv_expand(const GvRegs<BITS>& r, uint32_t one, uint32_t (&h)[8]) {
+  if constexpr (BITS == 2) {
+    const uint32_t w = r.w[CH];
+    const uint32_t b0 = w << 4, b1 = w << 2, b2 = w >> 4, b3 = w >> 6;
+    h[0] = and_or(b0, 0x00300030u, one); h[1] = and_or(b1, 0x00300030u, one);   // u=0: e=2
+    h[2] = and_or(b2, 0x00300030u, one); h[3] = and_or(b3, 0x00300030u, one);   // u=1: e=2
+    h[4] = and_or(b0, 0x03000300u, one); h[5] = and_or(b1, 0x03000300u, one);   // u=2: e=0
+    h[6] = and_or(b2, 0x03000300u, one); h[7] = and_or(b3, 0x03000300u, one);   // u=3: e=0
+  } else if constexpr (BITS == 4) {
+    // half-word nibbles (slot4): u%2 = 0 at bits 0 (row g) / 4 (row g+8), u%2 = 1 at 8 / 12.
+    // w<<2, w>>2 -> field at bits 2-5 (e = 2); w>>2, w>>6 -> bits 6-9 (e = 0).
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const uint32_t w = r.w[2 * CH + i];
+      const uint32_t c0 = w << 2, c1 = w >> 2, c2 = w >> 6;
+      h[4 * i + 0] = and_or(c0, 0x003C003Cu, one); h[4 * i + 1] = and_or(c1, 0x003C003Cu, one);
+      h[4 * i + 2] = and_or(c1, 0x03C003C0u, one); h[4 * i + 3] = and_or(c2, 0x03C003C0u, one);
+    }
+  } else {
+    expand_chunk<3, (CH & 1)>(r.w[CH], r.w[4 + (CH >> 1)], h);
+  }
+}
+
+template <int BITS, int NT8, int RBC, int D>
+__global__ void __launch_bounds__(GV_WARPS * 32)
+qgemv_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x, const float* __restrict__ scales,
+             const float* __restrict__ zeros, const __half* __restrict__ bias, __half* __restrict__ z, int M, int K,
+             int N) {
+  constexpr int TOK = 8 * NT8, ROWS = 16 * RBC, RLD = ROWS + 4, W = GV_WARPS;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int KSB = K >> 7, NRB = N >> 4;
+  const int ntiles = (NRB + RBC - 1) / RBC;
+  const int xld = K + GV_XPAD;
+  __half* xs = reinterpret_cast<__half*>(smem_raw);                                        // [M][xld]
+  float* red = reinterpret_cast<float*>(smem_raw + (((size_t)M * xld * sizeof(__half) + 15) & ~(size_t)15));  // [2][W][TOK][RLD]
+  float* red_st = red + 2 * W * TOK * RLD;                                                 // [W][2][TOK]: S, T
+
+  const int nround = (KSB - warp + W - 1) / W;            // k super-blocks of this warp: ks = warp + W*round
+  const int nround_pad = ((KSB + W - 1) / W + D - 1) / D * D;   // same for every warp; slot = round % D
+
+  // ---- the ring: slot d holds step (tile, round) with round % D == d ----
+  GvRegs<BITS> ring[D][RBC];
+  auto fetch = [&](int tile, int round, GvRegs<BITS> (&dst)[RBC]) {
+    if (tile < ntiles && round < nround) {
+      const int ks = warp + W * round;
+#pragma unroll
+      for (int r = 0; r < RBC; ++r) {
+        const int rb = min(tile * RBC + r, NRB - 1);      // tail tile: re-read a valid block, masked at the store
+        gv_load<BITS>(q + ((int64_t)rb * KSB + ks) * sb_words(BITS), lane, dst[r]);
+      }
+    }
+  };
+  int tile = blockIdx.x;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {                           // weights first: independent of the previous kernel
+    int ft = tile, fr = d;
+    if (fr >= nround_pad) { fr -= nround_pad; ft += gridDim.x; }
+    fetch(ft, fr, ring[d]);
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ---- stage the tokens once per CTA, pre-scaled per k position ----
+  {
+    const int cpr = K >> 3;
+    for (int tok = 0; tok < M; ++tok) {
+      const uint4* src = reinterpret_cast<const uint4*>(x + (int64_t)tok * K);
+      uint4* dst = reinterpret_cast<uint4*>(xs + (size_t)tok * xld);
+      for (int c = tid; c < cpr; c += W * 32) {
+        uint4 v = src[c];
+        if constexpr (Gv<BITS>::kRaw) {
+          if (gv_scale<BITS>(1) != H2_ONE) v.y = hmul2_u32(v.y, gv_scale<BITS>(1));
+          if (gv_scale<BITS>(2) != H2_ONE) v.z = hmul2_u32(v.z, gv_scale<BITS>(2));
+          if (gv_scale<BITS>(3) != H2_ONE) v.w = hmul2_u32(v.w, gv_scale<BITS>(3));
+        }
+        dst[c] = v;
+      }
+    }
+  }
+  __syncthreads();
+
+  const uint32_t one = opaque_u32(H2_ONE);
+  // constant A fragments of the token-sum MMA, k-steps 0 and 1: {row g, row g+8} x {k pair 2s, 2s+1}
+  const uint32_t cst[2][4] = {
+      {one, opaque_u32(gv_inv_scale<BITS>(0)), one, opaque_u32(gv_inv_scale<BITS>(1))},
+      {one, opaque_u32(gv_inv_scale<BITS>(2)), one, opaque_u32(gv_inv_scale<BITS>(3))}};
+  // epilogue ownership: thread -> output row erow of the tile, tokens etok + j*ETS
+  constexpr int ETS = (W * 32) / ROWS;                     // tokens covered per pass of the CTA
+  constexpr int EPT = (TOK + ETS - 1) / ETS;               // passes
+  const int erow = tid % ROWS, etok = tid / ROWS;
+  float S[EPT], T[EPT];
+  bool first = true;
+  int parity = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    // this tile's dequantisation parameters: requested now, used after the k loop
+    float e_sc = 0.f, e_ze = 0.f, e_bi = 0.f;
+    {
+      const int n = tile * ROWS + erow;
+      if (n < N && etok < M) {
+        e_sc = __ldg(scales + n);
+        e_ze = __ldg(zeros + n);
+        if (bias) e_bi = __half2float(__ldg(bias + n));
+      }
+    }
+    float acc[RBC][NT8][4];
+    float acc_st[NT8][4];
+#pragma unroll
+    for (int b = 0; b < NT8; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        acc_st[b][c] = 0.f;
+#pragma unroll
+        for (int a = 0; a < RBC; ++a) acc[a][b][c] = 0.f;
+      }
+
+    // FIRST (compile time): this CTA's first row tile also accumulates the token sums
+    auto run_tile = [&](auto first_c) {
+      constexpr bool FIRST = decltype(first_c)::value;
+      for (int round0 = 0; round0 < nround_pad; round0 += D) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const int round = round0 + d;
+          if (round < nround) {
+            const int ks = warp + W * round;
+            const __half* xk = xs + ks * 128 + 8 * t;
+            auto do_chunk = [&](auto chc) {
+              constexpr int CH = decltype(chc)::value;
+              uint32_t xb[NT8][4];
+#pragma unroll
+              for (int nt = 0; nt < NT8; ++nt) {
+                // token columns >= M re-read the last real token: their results are never stored
+                const uint4 v = *reinterpret_cast<const uint4*>(xk + (size_t)min(nt * 8 + g, M - 1) * xld + CH * 32);
+                xb[nt][0] = v.x; xb[nt][1] = v.y; xb[nt][2] = v.z; xb[nt][3] = v.w;
+              }
+#pragma unroll
+              for (int r = 0; r < RBC; ++r) {
+                uint32_t h[8];
+                gv_expand<BITS, CH>(ring[d][r], one, h);
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                  const uint32_t a[4] = {h[4 * s], h[4 * s + 1], h[4 * s + 2], h[4 * s + 3]};
+#pragma unroll
+                  for (int nt = 0; nt < NT8; ++nt) {
+                    const uint32_t b[2] = {xb[nt][2 * s], xb[nt][2 * s + 1]};
+                    mma16816(acc[r][nt], a, b);
+                  }
+                }
+              }
+              if constexpr (FIRST) {
+                // token sums on the tensor pipe, one MMA per k-step: rows 0-7 of the constant A tile are ones
+                // (-> T, the sum of the pre-scaled tokens), rows 8-15 undo the scale (-> S, the plain sum)
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                  for (int nt = 0; nt < NT8; ++nt) {
+                    const uint32_t b[2] = {xb[nt][2 * s], xb[nt][2 * s + 1]};
+                    mma16816(acc_st[nt], cst[s], b);
+                  }
+              }
+            };
+            do_chunk(std::integral_constant<int, 0>{});
+            do_chunk(std::integral_constant<int, 1>{});
+            do_chunk(std::integral_constant<int, 2>{});
+            do_chunk(std::integral_constant<int, 3>{});
+          }
+          // refill this slot with the step D ahead (possibly in this CTA's next row tile)
+          int ft = tile, fr = round + D;
+          if (fr >= nround_pad) { fr -= nround_pad; ft += gridDim.x; }
+          fetch(ft, fr, ring[d]);
+        }
+      }
+    };
+    if (first) run_tile(std::true_type{});
+    else run_tile(std::false_type{});
+
+    // ---- reduce the warps (each covered different k): red[tile parity][warp][tok][row] ----
+    float* redp = red + (parity ? W * TOK * RLD : 0);
+#pragma unroll
+    for (int r = 0; r < RBC; ++r)
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) {
+        float* b = redp + (warp * TOK + nt * 8 + 2 * t) * RLD + r * 16 + g;
+        b[0] = acc[r][nt][0];
+        b[RLD] = acc[r][nt][1];
+        b[8] = acc[r][nt][2];
+        b[RLD + 8] = acc[r][nt][3];
+      }
+    if (first && g == 0) {
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) {
+        float* b = red_st + warp * 2 * TOK + nt * 8 + 2 * t;
+        b[0] = acc_st[nt][2]; b[1] = acc_st[nt][3];          // rows 8-15: S
+        b[TOK] = acc_st[nt][0]; b[TOK + 1] = acc_st[nt][1];  // rows 0-7: T
+      }
+    }
+    __syncthreads();      // the only barrier of a tile: red[] alternates, so the next tile's writes cannot race
+
+    if (first) {          // every epilogue thread keeps the sums of its own tokens for all later tiles
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int tok = etok + j * ETS;
+        float s = 0.f, tt = 0.f;
+        if (tok < M) {
+#pragma unroll
+          for (int w = 0; w < W; ++w) {
+            s += red_st[w * 2 * TOK + tok];
+            tt += red_st[w * 2 * TOK + TOK + tok];
+          }
+        }
+        S[j] = s;
+        T[j] = Gv<BITS>::kRaw ? tt : 0.f;
+      }
+    }
+    {
+      const int n = tile * ROWS + erow;
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int tok = etok + j * ETS;
+        if (tok < M && n < N) {
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < W; ++w) s += redp[(w * TOK + tok) * RLD + erow];
+          float v = e_sc * (Gv<BITS>::kA1 * (s - T[j]) + Gv<BITS>::kA2 * S[j]) - e_ze * S[j] + e_bi;
+          z[(int64_t)tok * N + n] = __float2half_rn(v);
+        }
+      }
+    }
+    first = false;
+    parity ^= 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// int8 tensor-core path
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void imma16832(int (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+constexpr int GV_LIMBS = 3;            // bytes per token value: round(x * 2^22 / amax) in balanced base 256
+constexpr float GV_QMAX = 4194304.f;   // 2^22: the top limb stays within +-64
+
+// A registers of chunk CH: rows g (a0, a2) and g+8 (a1, a3; scaled by 4 / 16, undone in the epilogue)
+template <int BITS, int CH>
+__device__ __forceinline__ void gv_expand_i8(const GvRegs<BITS>& r, uint32_t (&a)[4]) {
+  if constexpr (BITS == 2) {
+    const uint32_t w = r.w[CH], w4 = w >> 4;
+    a[0] = w & 0x03030303u; a[1] = w & 0x0C0C0C0Cu; a[2] = w4 & 0x03030303u; a[3] = w4 & 0x0C0C0C0Cu;
+  } else {
+    const uint32_t w0 = r.w[2 * CH], w1 = r.w[2 * CH + 1];
+    a[0] = w0 & 0x0F0F0F0Fu; a[1] = w0 & 0xF0F0F0F0u; a[2] = w1 & 0x0F0F0F0Fu; a[3] = w1 & 0xF0F0F0F0u;
+  }
+}
+
+template <int BITS, int NT8, int RBC, int D>
+__global__ void __launch_bounds__(GV_WARPS * 32)
+qgemv_i8_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x, const float* __restrict__ scales,
+                const float* __restrict__ zeros, const __half* __restrict__ bias, __half* __restrict__ z, int M, int K,
+                int N) {
+  constexpr int COLS = 8 * NT8, ROWS = 16 * RBC, RLD = ROWS + 4, W = GV_WARPS;
+  constexpr float HI_ROW_SCALE = BITS == 2 ? 0.25f : 0.0625f;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int KSB = K >> 7, NRB = N >> 4;
+  const int ntiles = (NRB + RBC - 1) / RBC;
+  const int ncol = GV_LIMBS * M;                          // B columns in use: 3 per token
+  const int lld = K + 32;                                 // bytes; LDS.64 phases conflict-free
+  int8_t* limbs = reinterpret_cast<int8_t*>(smem_raw);                                     // [ncol][lld], slot order
+  int* red = reinterpret_cast<int*>(smem_raw + (((size_t)ncol * lld + 15) & ~(size_t)15));  // [2][W][COLS][RLD]
+  float* tokf = reinterpret_cast<float*>(red + 2 * W * COLS * RLD);                        // [M][2]: s_m, S_m
+  float* wred = tokf + 2 * 8;                                                              // [W][2] scratch
+
+  const int nround = (KSB - warp + W - 1) / W;
+  const int nround_pad = ((KSB + W - 1) / W + D - 1) / D * D;
+  GvRegs<BITS> ring[D][RBC];
+  auto fetch = [&](int tile, int round, GvRegs<BITS> (&dst)[RBC]) {
+    if (tile < ntiles && round < nround) {
+      const int ks = warp + W * round;
+#pragma unroll
+      for (int r = 0; r < RBC; ++r) {
+        const int rb = min(tile * RBC + r, NRB - 1);
+        gv_load<BITS>(q + ((int64_t)rb * KSB + ks) * sb_words(BITS), lane, dst[r]);
+      }
+    }
+  };
+  int tile = blockIdx.x;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {                           // weights first: independent of the previous kernel
+    int ft = tile, fr = d;
+    if (fr >= nround_pad) { fr -= nround_pad; ft += gridDim.x; }
+    fetch(ft, fr, ring[d]);
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ---- tokens -> three signed bytes each, once per CTA ----
+  const int cpr = K >> 3;
+  for (int tok = 0; tok < M; ++tok) {
+    const uint4* src = reinterpret_cast<const uint4*>(x + (int64_t)tok * K);
+    float amax = 0.f, sum = 0.f;
+    for (int c = tid; c < cpr; c += W * 32) {
+      const uint4 v = src[c];
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h2[i]);
+        amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+        sum += f.x + f.y;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (lane == 0) { wred[2 * warp] = amax; wred[2 * warp + 1] = sum; }
+    __syncthreads();
+    amax = 0.f; sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < W; ++w) { amax = fmaxf(amax, wred[2 * w]); sum += wred[2 * w + 1]; }   // same order everywhere
+    const float inv = amax > 0.f ? GV_QMAX / amax : 0.f;
+    if (tid == 0) { tokf[2 * tok] = amax / GV_QMAX; tokf[2 * tok + 1] = sum; }
+    for (int c = tid; c < cpr; c += W * 32) {
+      const uint4 v = src[c];                             // second read hits L1/L2
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+      int qv[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h2[i]);
+        qv[2 * i] = __float2int_rn(f.x * inv);
+        qv[2 * i + 1] = __float2int_rn(f.y * inv);
+      }
+      // balanced limbs, stored in slot order: byte s of a run <- k offset {0,2,1,3,4,6,5,7}[s]
+      uint32_t lb[GV_LIMBS][2] = {};
+#pragma unroll
+      for (int sidx = 0; sidx < 8; ++sidx) {
+        constexpr int PI[8] = {0, 2, 1, 3, 4, 6, 5, 7};
+        int v0 = qv[PI[sidx]];
+        const int lo = (int)(int8_t)(v0 & 0xFF);
+        v0 = (v0 - lo) >> 8;
+        const int mid = (int)(int8_t)(v0 & 0xFF);
+        const int hi = (v0 - mid) >> 8;
+        lb[0][sidx >> 2] |= (uint32_t)(hi & 0xFF) << (8 * (sidx & 3));
+        lb[1][sidx >> 2] |= (uint32_t)(mid & 0xFF) << (8 * (sidx & 3));
+        lb[2][sidx >> 2] |= (uint32_t)(lo & 0xFF) << (8 * (sidx & 3));
+      }
+#pragma unroll
+      for (int l = 0; l < GV_LIMBS; ++l)
+        *reinterpret_cast<uint2*>(limbs + (size_t)(GV_LIMBS * tok + l) * lld + 8 * c) = make_uint2(lb[l][0], lb[l][1]);
+    }
+    __syncthreads();                                      // wred reuse; also publishes the limbs
+  }
+
+  constexpr int ETS = (W * 32) / ROWS;
+  constexpr int EPT = (8 + ETS - 1) / ETS;                // tokens (<= 8 ever) per epilogue thread
+  const int erow = tid % ROWS, etok = tid / ROWS;
+  int parity = 0;
+  for (; tile < ntiles; tile += gridDim.x) {
+    float e_sc = 0.f, e_ze = 0.f, e_bi = 0.f;
+    {
+      const int n = tile * ROWS + erow;
+      if (n < N && etok < M) {
+        e_sc = __ldg(scales + n);
+        e_ze = __ldg(zeros + n);
+        if (bias) e_bi = __half2float(__ldg(bias + n));
+      }
+    }
+    int acc[RBC][NT8][4];
+#pragma unroll
+    for (int a = 0; a < RBC; ++a)
+#pragma unroll
+      for (int b = 0; b < NT8; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][b][c] = 0;
+
+    for (int round0 = 0; round0 < nround_pad; round0 += D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const int round = round0 + d;
+        if (round < nround) {
+          const int ks = warp + W * round;
+          const int8_t* lk = limbs + ks * 128 + 8 * t;
+          auto do_chunk = [&](auto chc) {
+            constexpr int CH = decltype(chc)::value;
+            uint32_t xb[NT8][2];
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt) {
+              // columns beyond the last limb re-read it: their results are never stored
+              const uint2 v = *reinterpret_cast<const uint2*>(lk + (size_t)min(nt * 8 + g, ncol - 1) * lld + CH * 32);
+              xb[nt][0] = v.x; xb[nt][1] = v.y;
+            }
+#pragma unroll
+            for (int r = 0; r < RBC; ++r) {
+              uint32_t a[4];
+              gv_expand_i8<BITS, CH>(ring[d][r], a);
+#pragma unroll
+              for (int nt = 0; nt < NT8; ++nt) imma16832(acc[r][nt], a, xb[nt]);
+            }
+          };
+          do_chunk(std::integral_constant<int, 0>{});
+          do_chunk(std::integral_constant<int, 1>{});
+          do_chunk(std::integral_constant<int, 2>{});
+          do_chunk(std::integral_constant<int, 3>{});
+        }
+        int ft = tile, fr = round + D;
+        if (fr >= nround_pad) { fr -= nround_pad; ft += gridDim.x; }
+        fetch(ft, fr, ring[d]);
+      }
+    }
+
+    // ---- reduce the warps: integer sums, order-independent ----
+    int* redp = red + (parity ? W * COLS * RLD : 0);
+#pragma unroll
+    for (int r = 0; r < RBC; ++r)
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) {
+        int* b = redp + (warp * COLS + nt * 8 + 2 * t) * RLD + r * 16 + g;
+        b[0] = acc[r][nt][0];
+        b[RLD] = acc[r][nt][1];
+        b[8] = acc[r][nt][2];
+        b[RLD + 8] = acc[r][nt][3];
+      }
+    __syncthreads();
+    {
+      const int n = tile * ROWS + erow;
+      const float rs = (erow & 8) ? HI_ROW_SCALE : 1.f;   // rows g+8 were masked in place, 4x / 16x too large
+#pragma unroll
+      for (int j = 0; j < EPT; ++j) {
+        const int tok = etok + j * ETS;
+        if (tok < M && n < N) {
+          float limb[GV_LIMBS];
+#pragma unroll
+          for (int l = 0; l < GV_LIMBS; ++l) {
+            int sacc = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) sacc += redp[(w * COLS + GV_LIMBS * tok + l) * RLD + erow];
+            limb[l] = (float)sacc;
+          }
+          const float dot = tokf[2 * tok] * rs * (65536.f * limb[0] + 256.f * limb[1] + limb[2]);   // sum_k c x
+          const float v = e_sc * dot - e_ze * tokf[2 * tok + 1] + e_bi;
+          z[(int64_t)tok * N + n] = __float2half_rn(v);
+        }
+      }
+    }
+    parity ^= 1;
+  }
+}
+
+int num_sms();
+
+template <int BITS, int NT8, int RBC, int D>
+static int launch_gv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M, cudaStream_t s) {
+  constexpr int TOK = 8 * NT8, ROWS = 16 * RBC, RLD = ROWS + 4;
+  const size_t xs_bytes = ((size_t)M * (d->K + GV_XPAD) * sizeof(__half) + 15) & ~(size_t)15;
+  const size_t smem = xs_bytes + (size_t)(2 * GV_WARPS * TOK * RLD + GV_WARPS * 2 * TOK) * sizeof(float);
+  auto kern = qgemv_kernel<BITS, NT8, RBC, D>;
+  // the attribute and the occupancy query cost more host time than the kernel runs: cache per (kernel, device)
+  static size_t attr_smem[64] = {0}, occ_smem[64] = {0};
+  static int occ[64] = {0};
+  int dev = 0;
+  QUIP_CUDA(cudaGetDevice(&dev));
+  dev &= 63;
+  if (smem > attr_smem[dev]) {
+    QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[dev] = smem;
+  }
+  const int tiles = ceil_div(d->N / 16, RBC);
+  int grid = tiles;
+  if (g_gv_persist) {
+    if (occ[dev] == 0 || occ_smem[dev] != smem) {
+      QUIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[dev], kern, GV_WARPS * 32, smem));
+      if (occ[dev] < 1) occ[dev] = 1;
+      occ_smem[dev] = smem;
+    }
+    if (grid > occ[dev] * num_sms()) grid = occ[dev] * num_sms();
+  }
+  kern<<<grid, GV_WARPS * 32, smem, s>>>(reinterpret_cast<const uint32_t*>(d->qweight), x, d->scales, d->zeros, bias,
+                                         z, M, d->K, d->N);
+  QUIP_LAUNCHED("qgemv_kernel");
+  return QUIP_OK;
+}
+
+template <int BITS, int NT8, int RBC, int D>
+static int launch_gv_i8(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M, cudaStream_t s) {
+  constexpr int COLS = 8 * NT8, ROWS = 16 * RBC, RLD = ROWS + 4;
+  const size_t limb_bytes = ((size_t)GV_LIMBS * M * (d->K + 32) + 15) & ~(size_t)15;
+  const size_t smem = limb_bytes + (size_t)(2 * GV_WARPS * COLS * RLD) * sizeof(int) + (size_t)(16 + 2 * GV_WARPS) * sizeof(float);
+  auto kern = qgemv_i8_kernel<BITS, NT8, RBC, D>;
+  static size_t attr_smem[64] = {0}, occ_smem[64] = {0};
+  static int occ[64] = {0};
+  int dev = 0;
+  QUIP_CUDA(cudaGetDevice(&dev));
+  dev &= 63;
+  if (smem > attr_smem[dev]) {
+    QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[dev] = smem;
+  }
+  const int tiles = ceil_div(d->N / 16, RBC);
+  int grid = tiles;
+  if (g_gv_persist) {
+    if (occ[dev] == 0 || occ_smem[dev] != smem) {
+      QUIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[dev], kern, GV_WARPS * 32, smem));
+      if (occ[dev] < 1) occ[dev] = 1;
+      occ_smem[dev] = smem;
+    }
+    if (grid > occ[dev] * num_sms()) grid = occ[dev] * num_sms();
+  }
+  kern<<<grid, GV_WARPS * 32, smem, s>>>(reinterpret_cast<const uint32_t*>(d->qweight), x, d->scales, d->zeros, bias,
+                                         z, M, d->K, d->N);
+  QUIP_LAUNCHED("qgemv_i8_kernel");
+  return QUIP_OK;
+}
+
+// shared memory the whole-K kernels need for M tokens; the caller falls back to the split-K kernel above this
+bool qgemv_fits(int K, int M) {
+  if (M > 8 || K < 128 * GV_WARPS) return false;
+  const size_t smem = (size_t)M * (K + GV_XPAD) * sizeof(__half) +
+                      (size_t)(2 * GV_WARPS * 8 * 36 + GV_WARPS * 16) * sizeof(float) + 16;
+  return smem <= 200 * 1024;
+}
+
+int qgemv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M, cudaStream_t s) {
+  QUIP_CHECK_ARG(M >= 1 && M <= 8, "qgemv handles 1..8 tokens (got %d)", M);
+  QUIP_CHECK_ARG(qgemv_fits(d->K, M), "qgemv: K=%d with %d tokens does not fit shared memory", d->K, M);
+  int rbc = g_gv_rbc;
+  if (rbc != 1 && rbc != 2) rbc = (d->N / 16 >= 4 * num_sms()) ? 2 : 1;
+  if (g_gv_int && d->bits != 3 && M <= 5) {
+    const int nt8 = M <= 2 ? 1 : 2;
+#define QUIP_GVI(B, T, DD)                                                                  \
+  if (d->bits == B && nt8 == T) {                                                           \
+    if (rbc == 2) return launch_gv_i8<B, T, 2, DD>(d, x, bias, z, M, s);                    \
+    return launch_gv_i8<B, T, 1, 2 * DD>(d, x, bias, z, M, s);                              \
+  }
+    QUIP_GVI(2, 1, 4) QUIP_GVI(2, 2, 4) QUIP_GVI(4, 1, 2) QUIP_GVI(4, 2, 2)
+#undef QUIP_GVI
+  }
+#define QUIP_GV(B, DD)                                                                      \
+  if (d->bits == B) {                                                                       \
+    if (rbc == 2) return launch_gv<B, 1, 2, DD>(d, x, bias, z, M, s);                       \
+    return launch_gv<B, 1, 1, 2 * DD>(d, x, bias, z, M, s);                                 \
+  }
+  QUIP_GV(2, 2) QUIP_GV(3, 2) QUIP_GV(4, 1)
+#undef QUIP_GV
+  set_error("qgemv: unsupported bits=%d", d->bits);
+  return QUIP_ERR_UNSUPPORTED;
+}
+
+}  // namespace quip

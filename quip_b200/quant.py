@@ -167,7 +167,8 @@ def _native_fields(N, K, bits, device):
     ch, t, pos = kk // 32, (kk % 32) // 8, kk % 8
     lane, e = g * 4 + t, pos % 2
     base = (rb * (K // 128) + ks) * _SB_WORDS[bits]
-    j = 2 * (pos // 2) + hi
+    u = pos // 2
+    j = 2 * ((u % 2) * 2 + u // 2) + hi
     if bits == 2:
         return [(base + lane * 4 + ch, 2 * j + 16 * e, 0, 2)]
     if bits == 4:

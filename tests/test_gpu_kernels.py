@@ -122,6 +122,38 @@ def test_qgemm_skinny_vs_oracle(bits, M, symmetric):
         assert _rel(z, want) < 3e-4, (bits, M, symmetric, N, K, _rel(z, want))
 
 
+@pytest.mark.parametrize('bits', [2, 3, 4])
+@pytest.mark.parametrize('M', [1, 2, 4, 5, 6, 8])
+@pytest.mark.parametrize('cfg', [dict(gv_int=1, gv_rbc=0), dict(gv_int=1, gv_rbc=2), dict(gv_int=0, gv_rbc=1),
+                                 dict(gv_int=1, gv_rbc=1, gv_persist=0)])
+def test_qgemv_whole_k_kernels(bits, M, cfg):
+    """The few-token kernels (int8 tensor path for <= 5 tokens, offset-free fp16 path above): odd numbers of k
+    super-blocks, ragged row tiles, a token with a huge outlier (the int8 path scales per token by amax) and an
+    all-zero token."""
+    from gpu_util import run_qgemm
+    from quip_b200 import _lib
+    lib = _lib.load()
+    try:
+        for k, v in cfg.items():
+            lib.quip_config(k.encode(), v)
+        for (N, K) in [(176, 11008), (272, 1024), (4096, 4096)]:
+            codes, scales, zeros, X, bias, want = _qgemm_case(bits, N, K, M, False, bits * 10 + M)
+            X = X.copy()
+            X[0, 7] = f16(3000.0)                      # outlier: amax/sigma ~ 1000
+            if M > 1:
+                X[M - 1, :] = 0
+            Qm = scales.astype(np.float64) * codes.astype(np.float64) - zeros.astype(np.float64)
+            want = X.astype(np.float64) @ Qm.T + bias.astype(np.float64)[None, :]
+            z, _ = run_qgemm(codes, scales, zeros, bits, X, path=1, bias=bias, symmetric=False)
+            assert not np.isnan(z.astype(f32)).any()
+            assert _rel(z, want) < 3e-4, (bits, M, cfg, N, K, _rel(z, want))
+            if M > 1:
+                np.testing.assert_allclose(z[M - 1].astype(f32), bias.astype(f32), atol=2e-3)
+    finally:
+        for k, v in dict(gv_int=1, gv_rbc=0, gv_persist=1).items():
+            lib.quip_config(k.encode(), v)
+
+
 def test_qgemm_skinny_large_M_loops():
     from gpu_util import run_qgemm
     codes, scales, zeros, X, bias, want = _qgemm_case(2, 256, 512, 100, False, 5)

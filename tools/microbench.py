@@ -19,12 +19,34 @@ DEV = 'cuda:0'
 ITERS = None
 
 
+GRAPH = False
+
+
 def timeit(fn, iters=50, warm=5):
     if ITERS:
         iters, warm = ITERS, 2
     for _ in range(warm):
         fn(0)
     torch.cuda.synchronize()
+    if GRAPH:
+        # replay `iters` back-to-back launches from one CUDA graph: GPU time without the Python/ctypes launch cost
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=side):
+                for i in range(iters):
+                    fn(i)
+        torch.cuda.current_stream().wait_stream(side)
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (3 * iters) * 1e3
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(iters):
@@ -118,9 +140,11 @@ def main():
     ap.add_argument('--what', default='qgemm,dense,pass,layer')
     ap.add_argument('--out', default=os.path.join(ROOT, 'gpurun_out', 'microbench.json'))
     ap.add_argument('--iters', type=int, default=0)
+    ap.add_argument('--graph', action='store_true', help='time CUDA-graph replays (GPU time, no host launch cost)')
     a = ap.parse_args()
-    global ITERS
+    global ITERS, GRAPH
     ITERS = a.iters or None
+    GRAPH = a.graph
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(
         os.path.join(ROOT, 'MEASURED_PEAKS.json')) else dict(hbm_gbs=6650.0, bf16_tflops=1590.0)
     res = []
@@ -139,6 +163,30 @@ def main():
         # a stacked matrix (32 x 11008 rows): the skinny kernel's steady-state bandwidth, launch ramp amortised
         res.append(bench_qgemm(32 * 11008, 4096, 1, 2, 1, 2, peaks)); print(res[-1], flush=True)
         res.append(bench_qgemm(32 * 11008, 4096, 16, 2, 1, 2, peaks)); print(res[-1], flush=True)
+    if 'gemv' in what:
+        lib = _lib.load()
+        keys = ('gemv', 'gv_int', 'gv_rbc', 'gv_persist')
+        defaults = dict(gemv=1, gv_int=1, gv_rbc=0, gv_persist=1)
+
+        def run(N, K, M, bits, copies, **cfg):
+            for k in keys:
+                lib.quip_config(k.encode(), cfg.get(k, defaults[k]))
+            r = bench_qgemm(N, K, M, bits, 1, copies, peaks); r.update(cfg); res.append(r)
+            print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()
+                   if k not in ('TFLOPs', 'tensor_frac', 'kind', 'path')}, flush=True)
+        for (N, K) in shapes + [(32 * 11008, 4096)]:
+            copies = max(2, int(300e6 // (N * K // 4)))
+            for M in (1, 2, 4, 8):
+                run(N, K, M, 2, copies, gemv=0)
+                for rbc in (1, 2):
+                    run(N, K, M, 2, copies, gv_int=1, gv_rbc=rbc)
+                    if M != 8:
+                        run(N, K, M, 2, copies, gv_int=0, gv_rbc=rbc)
+        for bits in (3, 4):
+            for g in (0, 1):
+                run(11008, 4096, 1, bits, 8, gemv=g)
+        for k in keys:
+            lib.quip_config(k.encode(), defaults[k])
     if 'prof_tc' in what:
         res.append(bench_qgemm(4096, 4096, 2048, 2, 2, 2, peaks)); print(res[-1], flush=True)
         res.append(bench_qgemm(11008, 4096, 2048, 2, 2, 2, peaks)); print(res[-1], flush=True)
