@@ -37,13 +37,36 @@ int qgemm_tc2(const QuipLinearDesc* d, const __half* x, const float* xsum, const
 int qgemm_ts(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
              cudaStream_t s);
 
-extern int g_gather_rows, g_pass_min_tiles;   // rot.cu
-extern int g_gv_rbc, g_gv_persist, g_gv_int;  // qgemv.cu
+extern int g_gather_rows, g_pass_min_tiles, g_fewtok;   // rot.cu
+extern int g_gv_rbc, g_gv_persist, g_gv_int, g_gv_tma, g_gv_cw;  // qgemv.cu
 
 // tuning knobs (quip_config)
 static int g_use_tc2 = 0;        // route big-M contractions to the 2-CTA kernel
 static int g_use_ts = 0;         // route 2-bit big-M contractions to the TS-mode (A in TMEM) kernel
+static int g_pdl = 1;            // few-token kernels: programmatic dependent launch (weights prefetched under the previous kernel)
 static int g_use_gemv = 1;       // few-token contractions: whole-K qgemv kernel (0: the split-K kernel)
+
+// Launch with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in
+// the stream drains; everything it does before griddepcontrol.wait must be independent of that predecessor.
+int launch_pdl(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelExC(&cfg, kern, args);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("kernel launch failed: %s", cudaGetErrorString(e));
+    return QUIP_ERR_CUDA;
+  }
+  return QUIP_OK;
+}
 
 constexpr size_t WS_HEADER = 16 * 1024;     // split-K arrival counters; must be zero on first use, left zero
 constexpr int SKINNY_MAX_M = 32;
@@ -159,8 +182,12 @@ extern "C" int quip_config(const char* key, int value) {
   QUIP_CHECK_ARG(key != nullptr, "null key");
   if (!strcmp(key, "tc2")) { g_use_tc2 = value; return QUIP_OK; }
   if (!strcmp(key, "ts")) { g_use_ts = value; return QUIP_OK; }
+  if (!strcmp(key, "pdl")) { g_pdl = value; return QUIP_OK; }
+  if (!strcmp(key, "fewtok")) { g_fewtok = value; return QUIP_OK; }
   if (!strcmp(key, "gemv")) { g_use_gemv = value; return QUIP_OK; }
   if (!strcmp(key, "gv_rbc")) { g_gv_rbc = value; return QUIP_OK; }
+  if (!strcmp(key, "gv_cw")) { g_gv_cw = value; return QUIP_OK; }
+  if (!strcmp(key, "gv_tma")) { g_gv_tma = value; return QUIP_OK; }
   if (!strcmp(key, "gv_int")) { g_gv_int = value; return QUIP_OK; }
   if (!strcmp(key, "gv_persist")) { g_gv_persist = value; return QUIP_OK; }
   if (!strcmp(key, "gather_rows")) { g_gather_rows = value; return QUIP_OK; }

@@ -30,7 +30,7 @@
 // counters or fences.  The packed words of the first D steps are requested before anything else (they do
 // not depend on the previous kernel: with programmatic dependent launch they are in flight while it
 // drains), then the tokens are staged, then a D-deep register ring keeps D x RBC x 512 B per warp in flight.
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace quip {
 
@@ -39,6 +39,8 @@ constexpr int GV_XPAD = 32;            // halves; makes the 8-lane LDS.128 phase
 
 int g_gv_rbc = 0;                      // quip_config("gv_rbc", r): row blocks per CTA tile (0 = heuristic)
 int g_gv_int = 1;                      // quip_config("gv_int", 0): fp16 tensor path for every token count
+int g_gv_tma = 1;                      // quip_config("gv_tma", 0): register-ring variant of the int8 path
+int g_gv_cw = 16;                      // quip_config("gv_cw", 8|16): consumer warps of the bulk-copy kernel
 int g_gv_persist = 1;                  // quip_config("gv_persist", 0): one CTA per row tile instead of a persistent grid
 
 template <int BITS>
@@ -141,7 +143,7 @@ qgemv_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x, const
              const float* __restrict__ zeros, const __half* __restrict__ bias, __half* __restrict__ z, int M, int K,
              int N) {
   constexpr int TOK = 8 * NT8, ROWS = 16 * RBC, RLD = ROWS + 4, W = GV_WARPS;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int KSB = K >> 7, NRB = N >> 4;
   const int ntiles = (NRB + RBC - 1) / RBC;
@@ -377,7 +379,7 @@ qgemv_i8_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x, co
                 int N) {
   constexpr int COLS = 8 * NT8, ROWS = 16 * RBC, RLD = ROWS + 4, W = GV_WARPS;
   constexpr float HI_ROW_SCALE = BITS == 2 ? 0.25f : 0.0625f;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int KSB = K >> 7, NRB = N >> 4;
   const int ntiles = (NRB + RBC - 1) / RBC;
@@ -564,7 +566,293 @@ qgemv_i8_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// int8 path, bulk-copy fed and warp specialised (the default).  The register ring above ties the bytes in
+// flight to the progress of the very warps that consume them: a warp that waits (barrier, epilogue, a slow
+// neighbour) stops requesting, and the profile shows every warp stalled on its own loads at 40 % of HBM.
+// Here one producer thread streams the packed words with cp.async.bulk (1-D TMA) into a shared-memory ring
+// of 16-KiB stages, up to ~190 KiB in flight per SM whatever the consumers do; eight consumer warps take
+// their super-blocks of a stage with one conflict-free LDS.128 each; a ninth warp owns the epilogue, fed
+// through a double-buffered reduction buffer with its own mbarrier pair, so consumer warps never wait for
+// one another: producer -> consumers -> epilogue are three decoupled stages.
+//   stage  = up to 32 consecutive super-blocks of one row block (K <= 4096: its whole k run)
+//   tile   = RBC row blocks x all their stages; static tile -> CTA schedule (tile = blockIdx + i * grid)
+// ---------------------------------------------------------------------------------------------
+constexpr int gt_threads(int cw) { return (cw + 2) * 32; }   // consumer warps + producer warp + epilogue warp
+constexpr int GT_STAGE_SB = 32;                    // super-blocks per ring stage
+
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+template <int CW>
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(CW * 32) : "memory"); }
+
+template <int BITS>
+__device__ __forceinline__ void gv_lds(const uint32_t* sb, int lane, GvRegs<BITS>& r) {
+  const uint4 a = *reinterpret_cast<const uint4*>(sb + lane * 4);
+  r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+  if constexpr (BITS == 4) {
+    const uint4 b = *reinterpret_cast<const uint4*>(sb + 128 + lane * 4);
+    r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
+  }
+}
+
+template <int BITS, int NT8, int RBC, int CW>
+__global__ void __launch_bounds__(gt_threads(CW))
+qgemv_i8_tma_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x, const float* __restrict__ scales,
+                    const float* __restrict__ zeros, const __half* __restrict__ bias, __half* __restrict__ z, int M,
+                    int K, int N, int NS) {
+  constexpr int COLS = 8 * NT8, ROWS = 16 * RBC, RLD = ROWS + 4, W = CW;
+  constexpr float HI_ROW_SCALE = BITS == 2 ? 0.25f : 0.0625f;
+  constexpr uint32_t STAGE_BYTES = GT_STAGE_SB * sb_words(BITS) * 4;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int KSB = K >> 7, NRB = N >> 4;
+  const int ntiles = (NRB + RBC - 1) / RBC;
+  const int npiece = (KSB + GT_STAGE_SB - 1) / GT_STAGE_SB;
+  const int SP = (KSB + npiece - 1) / npiece;             // super-blocks per stage (last piece may be shorter)
+  const int ncol = GV_LIMBS * M;
+  const int lld = K + 32;
+
+  unsigned char* ring = smem_raw;                                                          // [NS][STAGE_BYTES]
+  int8_t* limbs = reinterpret_cast<int8_t*>(ring + (size_t)NS * STAGE_BYTES);              // [ncol][lld]
+  int* red = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(limbs) + (((size_t)ncol * lld + 15) & ~(size_t)15));
+  float* tokf = reinterpret_cast<float*>(red + 2 * W * COLS * RLD);                        // [8][2]: s_m, S_m
+  float* wred = tokf + 16;                                                                 // [W][2]
+  uint64_t* full = reinterpret_cast<uint64_t*>(wred + 2 * W);                              // [NS]
+  uint64_t* empty = full + NS;                                                             // [NS]
+  uint64_t* red_full = empty + NS;                                                         // [2]
+  uint64_t* red_empty = red_full + 2;                                                      // [2]
+
+  if (tid == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], W); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&red_full[i], W); mbar_init(&red_empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == W) {
+    // ===================== producer: one thread, runs ahead by the whole ring =====================
+    if (lane == 0) {
+      int slot = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x)
+        for (int piece = 0; piece < npiece; ++piece) {
+          const int sb0 = piece * SP;
+          const uint32_t bytes = (uint32_t)(min(KSB, sb0 + SP) - sb0) * sb_words(BITS) * 4u;
+#pragma unroll
+          for (int r = 0; r < RBC; ++r) {
+            mbar_wait(&empty[slot], ph ^ 1u);
+            const int rb = min(tile * RBC + r, NRB - 1);
+            mbar_arrive_expect_tx(&full[slot], bytes);
+            bulk_load_1d(ring + (size_t)slot * STAGE_BYTES, q + ((int64_t)rb * KSB + sb0) * sb_words(BITS), bytes,
+                         &full[slot]);
+            if (++slot == NS) { slot = 0; ph ^= 1u; }
+          }
+        }
+    }
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    return;
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");      // x is read, z written only after the previous kernel
+
+  if (warp == W + 1) {
+    // ===================== epilogue warp =====================
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+      const int parity = (int)(tcount & 1u);
+      const uint32_t ph = (tcount >> 1) & 1u;
+      const int* redp = red + (parity ? W * COLS * RLD : 0);
+      // this tile's dequantisation parameters travel while the consumers are still multiplying
+      constexpr int OPL = (5 * ROWS + 31) / 32;           // outputs per lane at the most tokens this path takes
+      float e_sc[OPL], e_ze[OPL], e_bi[OPL];
+#pragma unroll
+      for (int j = 0; j < OPL; ++j) {
+        const int o = lane + 32 * j, n = tile * ROWS + o % ROWS;
+        e_sc[j] = e_ze[j] = e_bi[j] = 0.f;
+        if (o < M * ROWS && n < N) {
+          e_sc[j] = __ldg(scales + n);
+          e_ze[j] = __ldg(zeros + n);
+          if (bias) e_bi[j] = __half2float(__ldg(bias + n));
+        }
+      }
+      mbar_wait(&red_full[parity], ph);
+#pragma unroll
+      for (int j = 0; j < OPL; ++j) {
+        const int o = lane + 32 * j, tok = o / ROWS, row = o % ROWS, n = tile * ROWS + row;
+        if (o < M * ROWS && n < N) {
+          float limb[GV_LIMBS];
+#pragma unroll
+          for (int l = 0; l < GV_LIMBS; ++l) {
+            int sacc = 0;
+#pragma unroll
+            for (int w = 0; w < W; ++w) sacc += redp[(w * COLS + GV_LIMBS * tok + l) * RLD + row];
+            limb[l] = (float)sacc;
+          }
+          const float rs = (row & 8) ? HI_ROW_SCALE : 1.f;
+          const float dot = tokf[2 * tok] * rs * (65536.f * limb[0] + 256.f * limb[1] + limb[2]);
+          z[(int64_t)tok * N + n] = __float2half_rn(e_sc[j] * dot - e_ze[j] * tokf[2 * tok + 1] + e_bi[j]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&red_empty[parity]);
+    }
+    return;
+  }
+
+  // ===================== consumer warps =====================
+  // ---- tokens -> three signed bytes each, once per CTA (the ring fills meanwhile) ----
+  const int cpr = K >> 3;
+  const int ctid = tid;                                   // consumers are threads 0 .. 255
+  for (int tok = 0; tok < M; ++tok) {
+    const uint4* src = reinterpret_cast<const uint4*>(x + (int64_t)tok * K);
+    float amax = 0.f, sum = 0.f;
+    for (int c = ctid; c < cpr; c += W * 32) {
+      const uint4 v = src[c];
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h2[i]);
+        amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
+        sum += f.x + f.y;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (lane == 0) { wred[2 * warp] = amax; wred[2 * warp + 1] = sum; }
+    consumer_sync<CW>();
+    amax = 0.f; sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < W; ++w) { amax = fmaxf(amax, wred[2 * w]); sum += wred[2 * w + 1]; }
+    const float inv = amax > 0.f ? GV_QMAX / amax : 0.f;
+    if (ctid == 0) { tokf[2 * tok] = amax / GV_QMAX; tokf[2 * tok + 1] = sum; }
+    for (int c = ctid; c < cpr; c += W * 32) {
+      const uint4 v = src[c];
+      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+      int qv[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h2[i]);
+        qv[2 * i] = __float2int_rn(f.x * inv);
+        qv[2 * i + 1] = __float2int_rn(f.y * inv);
+      }
+      uint32_t lb[GV_LIMBS][2] = {};
+#pragma unroll
+      for (int sidx = 0; sidx < 8; ++sidx) {
+        constexpr int PI[8] = {0, 2, 1, 3, 4, 6, 5, 7};
+        int v0 = qv[PI[sidx]];
+        const int lo = (int)(int8_t)(v0 & 0xFF);
+        v0 = (v0 - lo) >> 8;
+        const int mid = (int)(int8_t)(v0 & 0xFF);
+        const int hi = (v0 - mid) >> 8;
+        lb[0][sidx >> 2] |= (uint32_t)(hi & 0xFF) << (8 * (sidx & 3));
+        lb[1][sidx >> 2] |= (uint32_t)(mid & 0xFF) << (8 * (sidx & 3));
+        lb[2][sidx >> 2] |= (uint32_t)(lo & 0xFF) << (8 * (sidx & 3));
+      }
+#pragma unroll
+      for (int l = 0; l < GV_LIMBS; ++l)
+        *reinterpret_cast<uint2*>(limbs + (size_t)(GV_LIMBS * tok + l) * lld + 8 * c) = make_uint2(lb[l][0], lb[l][1]);
+    }
+    consumer_sync<CW>();
+  }
+
+  int slot = 0;                                           // ring position, advanced like the producer's
+  uint32_t ph = 0, tcount = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++tcount) {
+    // two accumulator chains per (row block, column group): chunks 0,2 and 1,3 -- an IMMA waits ~30 cycles for
+    // the one it accumulates onto, and with a handful of warps per scheduler that latency is the whole budget
+    int acc[RBC][NT8][2][4];
+#pragma unroll
+    for (int a = 0; a < RBC; ++a)
+#pragma unroll
+      for (int b = 0; b < NT8; ++b)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[a][b][0][c] = acc[a][b][1][c] = 0;
+
+    for (int piece = 0; piece < npiece; ++piece) {
+      const int sb0 = piece * SP;
+      const int nsb = min(KSB, sb0 + SP) - sb0;
+      const unsigned char* stage[RBC];
+      uint64_t* done[RBC];
+#pragma unroll
+      for (int r = 0; r < RBC; ++r) {
+        mbar_wait(&full[slot], ph);
+        stage[r] = ring + (size_t)slot * STAGE_BYTES;
+        done[r] = &empty[slot];
+        if (++slot == NS) { slot = 0; ph ^= 1u; }
+      }
+      GvRegs<BITS> cur[RBC], nxt[RBC];
+      if (warp < nsb) {
+#pragma unroll
+        for (int r = 0; r < RBC; ++r)
+          gv_lds<BITS>(reinterpret_cast<const uint32_t*>(stage[r]) + (size_t)warp * sb_words(BITS), lane, cur[r]);
+      }
+      for (int i = warp; i < nsb; i += W) {
+        if (i + W < nsb) {                                // next super-block's words travel under this one's math
+#pragma unroll
+          for (int r = 0; r < RBC; ++r)
+            gv_lds<BITS>(reinterpret_cast<const uint32_t*>(stage[r]) + (size_t)(i + W) * sb_words(BITS), lane, nxt[r]);
+        }
+        const int8_t* lk = limbs + (sb0 + i) * 128 + 8 * t;
+        uint32_t xb[4][NT8][2];
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+          for (int nt = 0; nt < NT8; ++nt) {
+            const uint2 v = *reinterpret_cast<const uint2*>(lk + (size_t)min(nt * 8 + g, ncol - 1) * lld + ch * 32);
+            xb[ch][nt][0] = v.x; xb[ch][nt][1] = v.y;
+          }
+        auto do_chunk = [&](auto chc) {
+          constexpr int CH = decltype(chc)::value;
+#pragma unroll
+          for (int r = 0; r < RBC; ++r) {
+            uint32_t a[4];
+            gv_expand_i8<BITS, CH>(cur[r], a);
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt) imma16832(acc[r][nt][CH & 1], a, xb[CH][nt]);
+          }
+        };
+        do_chunk(std::integral_constant<int, 0>{});
+        do_chunk(std::integral_constant<int, 1>{});
+        do_chunk(std::integral_constant<int, 2>{});
+        do_chunk(std::integral_constant<int, 3>{});
+#pragma unroll
+        for (int r = 0; r < RBC; ++r) cur[r] = nxt[r];
+      }
+      __syncwarp();
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < RBC; ++r) mbar_arrive(done[r]);
+      }
+    }
+
+    // ---- hand the partial sums to the epilogue warp ----
+    const int parity = (int)(tcount & 1u);
+    mbar_wait(&red_empty[parity], ((tcount >> 1) & 1u) ^ 1u);
+    int* redp = red + (parity ? W * COLS * RLD : 0);
+#pragma unroll
+    for (int r = 0; r < RBC; ++r)
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) {
+        int* b = redp + (warp * COLS + nt * 8 + 2 * t) * RLD + r * 16 + g;
+        b[0] = acc[r][nt][0][0] + acc[r][nt][1][0];
+        b[RLD] = acc[r][nt][0][1] + acc[r][nt][1][1];
+        b[8] = acc[r][nt][0][2] + acc[r][nt][1][2];
+        b[RLD + 8] = acc[r][nt][0][3] + acc[r][nt][1][3];
+      }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&red_full[parity]);
+  }
+}
+
 int num_sms();
+int launch_pdl(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args);   // api.cu
 
 template <int BITS, int NT8, int RBC, int D>
 static int launch_gv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M, cudaStream_t s) {
@@ -629,6 +917,45 @@ static int launch_gv_i8(const QuipLinearDesc* d, const __half* x, const __half* 
   return QUIP_OK;
 }
 
+template <int BITS, int NT8, int RBC, int CW>
+static int launch_gv_i8_tma(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M,
+                            cudaStream_t s) {
+  constexpr int COLS = 8 * NT8, ROWS = 16 * RBC, RLD = ROWS + 4;
+  constexpr size_t STAGE_BYTES = (size_t)GT_STAGE_SB * sb_words(BITS) * 4;
+  const size_t limb_bytes = ((size_t)GV_LIMBS * M * (d->K + 32) + 15) & ~(size_t)15;
+  const size_t fixed = limb_bytes + (size_t)(2 * CW * COLS * RLD) * sizeof(int) + (size_t)(16 + 2 * CW) * sizeof(float);
+  const size_t budget = 227 * 1024 - 256;
+  int ns = fixed + 64 < budget ? (int)((budget - fixed - 64) / (STAGE_BYTES + 16)) : 0;
+  if (ns > 12) ns = 12;
+  QUIP_CHECK_ARG(ns >= 2 * RBC, "qgemv: K=%d with %d tokens leaves no room for the weight ring", d->K, M);
+  const size_t smem = (size_t)ns * STAGE_BYTES + fixed + (size_t)(2 * ns + 4) * sizeof(uint64_t);
+  auto kern = qgemv_i8_tma_kernel<BITS, NT8, RBC, CW>;
+  static size_t attr_smem[64] = {0};
+  int dev = 0;
+  QUIP_CUDA(cudaGetDevice(&dev));
+  dev &= 63;
+  if (smem > attr_smem[dev]) {
+    QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[dev] = smem;
+  }
+  const int tiles = ceil_div(d->N / 16, RBC);
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  const uint32_t* qw = reinterpret_cast<const uint32_t*>(d->qweight);
+  const float *sc = d->scales, *ze = d->zeros;
+  int K = d->K, N = d->N;
+  void* args[] = {(void*)&qw, (void*)&x, (void*)&sc, (void*)&ze, (void*)&bias, (void*)&z, (void*)&M, (void*)&K, (void*)&N, (void*)&ns};
+  if (int e = launch_pdl((const void*)kern, dim3(grid), dim3(gt_threads(CW)), smem, s, args)) return e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QUIP_OK;
+}
+
+// does the bulk-copy kernel have room for at least a minimal ring next to the token bytes?
+static bool gv_tma_fits(int K, int M, int bits, int nt8, int rbc, int cw) {
+  const size_t stage = (size_t)GT_STAGE_SB * sb_words(bits) * 4;
+  const size_t fixed = (size_t)GV_LIMBS * M * (K + 32) + (size_t)(2 * cw * 8 * nt8 * (16 * rbc + 4)) * 4 + 512;
+  return fixed + (size_t)(2 * rbc + 2) * (stage + 16) <= (size_t)227 * 1024 - 256;
+}
+
 // shared memory the whole-K kernels need for M tokens; the caller falls back to the split-K kernel above this
 bool qgemv_fits(int K, int M) {
   if (M > 8 || K < 128 * GV_WARPS) return false;
@@ -644,6 +971,26 @@ int qgemv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* 
   if (rbc != 1 && rbc != 2) rbc = (d->N / 16 >= 4 * num_sms()) ? 2 : 1;
   if (g_gv_int && d->bits != 3 && M <= 5) {
     const int nt8 = M <= 2 ? 1 : 2;
+    if (g_gv_tma) {
+      int trbc = g_gv_rbc;
+      if (trbc != 1 && trbc != 2) trbc = 2;
+      int cw = g_gv_cw == 8 ? 8 : 16;
+      if (cw == 16 && !gv_tma_fits(d->K, M, d->bits, nt8, trbc, 16)) cw = 8;      // smaller reduction buffers
+      if (trbc == 2 && !gv_tma_fits(d->K, M, d->bits, nt8, 2, cw)) trbc = 1;
+      if (gv_tma_fits(d->K, M, d->bits, nt8, trbc, cw)) {
+#define QUIP_GVT(B, T)                                                                      \
+  if (d->bits == B && nt8 == T) {                                                           \
+    if (cw == 8) {                                                                          \
+      if (trbc == 2) return launch_gv_i8_tma<B, T, 2, 8>(d, x, bias, z, M, s);              \
+      return launch_gv_i8_tma<B, T, 1, 8>(d, x, bias, z, M, s);                             \
+    }                                                                                       \
+    if (trbc == 2) return launch_gv_i8_tma<B, T, 2, 16>(d, x, bias, z, M, s);               \
+    return launch_gv_i8_tma<B, T, 1, 16>(d, x, bias, z, M, s);                              \
+  }
+        QUIP_GVT(2, 1) QUIP_GVT(2, 2) QUIP_GVT(4, 1) QUIP_GVT(4, 2)
+#undef QUIP_GVT
+      }
+    }
 #define QUIP_GVI(B, T, DD)                                                                  \
   if (d->bits == B && nt8 == T) {                                                           \
     if (rbc == 2) return launch_gv_i8<B, T, 2, DD>(d, x, bias, z, M, s);                    \

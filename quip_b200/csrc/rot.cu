@@ -18,6 +18,7 @@
 namespace quip {
 
 int g_gather_rows = 0;        // quip_config("gather_rows", R)
+int g_fewtok = 1;              // quip_config("fewtok", 0): route <= 8 tokens through the many-token kernels
 int g_pass_min_tiles = 4;     // quip_config("pass_min_tiles", t): token tiles per CTA in the small-block passes
 
 // ----------------------------------------------------------------------------------------------
@@ -396,6 +397,15 @@ static int launch_gather(const __half* in, __half* out, int64_t M, int n, const 
   return QUIP_OK;
 }
 
+namespace quip {
+bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n);
+int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s);
+int gather_fewtok(const __half* in, __half* out, int64_t M, int n, const int32_t* idx, const float* scale,
+                  const __half* bias, cudaStream_t s);
+int pass_big_tc(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s);
+int launch_small_fast(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s, bool* handled);
+}
+
 extern "C" int quip_gather(const void* in, void* out, int64_t M, int32_t n, const int32_t* idx,
                            const float* scale, const void* bias, void* stream) {
   QUIP_CHECK_ARG(in && out && M > 0 && n > 0 && n % 8 == 0, "gather: bad arguments (M=%lld n=%d)", (long long)M, n);
@@ -405,6 +415,7 @@ extern "C" int quip_gather(const void* in, void* out, int64_t M, int32_t n, cons
   const __half* i = (const __half*)in;
   __half* o = (__half*)out;
   const __half* b = (const __half*)bias;
+  if (g_fewtok && M <= 8) return gather_fewtok(i, o, M, n, idx, scale, b, s);
   // rows per CTA: share the index vector across rows, but keep several waves of CTAs so that one CTA's load
   // phase overlaps another's permute phase
   const size_t row = (size_t)n * sizeof(__half);
@@ -421,11 +432,6 @@ extern "C" int quip_rowsum(const void* x, float* xsum, int64_t M, int32_t K, voi
   rowsum_kernel<<<ceil_div(M, 8), 256, 0, (cudaStream_t)stream>>>((const __half*)x, xsum, M, K);
   QUIP_LAUNCHED("rowsum_kernel");
   return QUIP_OK;
-}
-
-namespace quip {
-int pass_big_tc(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s);
-int launch_small_fast(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s, bool* handled);
 }
 
 template <int P>
@@ -453,6 +459,7 @@ extern "C" int quip_rot_pass(const QuipPass* ps, const void* in_, void* out_, in
   const __half* in = (const __half*)in_;
   __half* out = (__half*)out_;
   const int p = ps->p;
+  if (impl == 0 && g_fewtok && pass_fewtok_ok(ps, M, n)) return pass_fewtok(ps, in, out, M, n, s);
   bool small_ok = p <= 64;
   bool big_ok = p > 64 && !ps->strided && p % 8 == 0 && n % 8 == 0;
   if (impl != 1 && small_ok) {

@@ -1,0 +1,166 @@
+// Block-diagonal passes and the index/scale/bias gather for a handful of tokens (decode, M <= 8).
+//
+// With one token a pass of the incoherence transform (reference method.py:46-67, one stage of
+// mul_ortho_butterfly) is a batch of matrix-vector products whose cost is reading the factors once:
+// 0.5 MiB per pass at n = 4096, 15 MiB for the sixteen 688 x 688 blocks of an 11008 side -- more bytes
+// than the packed weights they surround.  The many-token kernels (rot_small.cu, qgemm_tc.cu DENSE) keep
+// factors resident and stream tokens; at M = 1 they run a handful of CTAs.  Here the roles flip, as in
+// qgemv.cu: the factor is the streamed A operand of mma.sync.m16n8k16, read straight from its row-major
+// array (a lane takes 8 bytes of rows g and g+8 per 16 k: full 32-byte sectors, no shared memory), the
+// tokens are the 8-wide B operand.
+//
+// Task = (block, 16 output rows, k part): the k range of a row tile is cut into parts of at most
+// FT_STEPS x 16 so that a warp requests everything it will ever read before its first MMA; the parts of a
+// row tile sit in one CTA and are summed through shared memory in a fixed order.  All factor loads are
+// issued before griddepcontrol.wait: under programmatic dependent launch they overlap the previous kernel.
+#include "common.cuh"
+
+namespace quip {
+
+constexpr int FT_WARPS = 8;
+constexpr int FT_STEPS = 12;           // k16 steps per task: 12 x (2 x 8 B) per lane in flight
+
+__global__ void __launch_bounds__(FT_WARPS * 32)
+pass_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, const __half* __restrict__ F, int M, int n,
+                   int p, int nblk, int strided, int shared, int kparts, int steps_per_part) {
+  __shared__ float red[FT_WARPS][16][9];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int rtiles = p >> 4;                               // 16-row tiles per block
+  const int groups_per_cta = FT_WARPS / kparts;            // (block, row tile) pairs per CTA
+  const int grp = warp / kparts, part = warp % kparts;
+  const int64_t task = (int64_t)blockIdx.x * groups_per_cta + grp;
+  const bool live = task < (int64_t)nblk * rtiles;
+  const int b = live ? (int)(task / rtiles) : 0, rt = live ? (int)(task % rtiles) : 0;
+  const int ksteps = p >> 4;
+  const int s0 = part * steps_per_part, s1 = min(ksteps, s0 + steps_per_part);
+
+  // ---- factor rows g and g+8 of this tile: everything requested up front (weights: no dependency) ----
+  const __half* frow = F + ((int64_t)(shared ? 0 : b) * p + rt * 16 + g) * p + 4 * t;
+  uint2 a_lo[FT_STEPS], a_hi[FT_STEPS];
+#pragma unroll
+  for (int s = 0; s < FT_STEPS; ++s) {
+    a_lo[s] = make_uint2(0u, 0u);
+    a_hi[s] = make_uint2(0u, 0u);
+    if (live && s0 + s < s1) {
+      a_lo[s] = ldg_nc_v2(frow + (s0 + s) * 16);
+      a_hi[s] = ldg_nc_v2(frow + (int64_t)8 * p + (s0 + s) * 16);
+    }
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ---- tokens: lane (g, t) needs x[token g][k = 16 s + 4 t .. +3]; columns >= M re-read the last token ----
+  const __half* xrow = in + (int64_t)min(g, M - 1) * n;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int s = 0; s < FT_STEPS; ++s) {
+    if (s0 + s < s1) {
+      const int j = (s0 + s) * 16 + 4 * t;
+      uint32_t bfrag[2];
+      if (strided) {
+        const __half* xp = xrow + (int64_t)j * nblk + b;
+        const uint32_t h0 = __half_as_ushort(__ldg(xp)), h1 = __half_as_ushort(__ldg(xp + nblk));
+        const uint32_t h2 = __half_as_ushort(__ldg(xp + 2 * (int64_t)nblk)), h3 = __half_as_ushort(__ldg(xp + 3 * (int64_t)nblk));
+        bfrag[0] = h0 | (h1 << 16);
+        bfrag[1] = h2 | (h3 << 16);
+      } else {
+        const uint2 v = *reinterpret_cast<const uint2*>(xrow + (int64_t)b * p + j);
+        bfrag[0] = v.x; bfrag[1] = v.y;
+      }
+      // k relabelled so that a lane's four consecutive k are MMA slots (2t, 2t+1, 2t+8, 2t+9) on both operands
+      const uint32_t a[4] = {a_lo[s].x, a_hi[s].x, a_lo[s].y, a_hi[s].y};
+      mma16816(acc, a, bfrag);
+    }
+  }
+
+  // ---- sum the k parts in a fixed order, store rows g / g+8 for tokens 2t, 2t+1 ----
+  if (kparts > 1) {
+    red[warp][g][2 * t] = acc[0]; red[warp][g][2 * t + 1] = acc[1];
+    red[warp][g + 8][2 * t] = acc[2]; red[warp][g + 8][2 * t + 1] = acc[3];
+    __syncthreads();
+    if (part != 0) return;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = 0.f;
+    for (int q = 0; q < kparts; ++q) {
+      acc[0] += red[warp + q][g][2 * t]; acc[1] += red[warp + q][g][2 * t + 1];
+      acc[2] += red[warp + q][g + 8][2 * t]; acc[3] += red[warp + q][g + 8][2 * t + 1];
+    }
+  }
+  if (!live) return;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int tok = 2 * t + (c & 1), i = rt * 16 + g + 8 * (c >> 1);
+    if (tok < M) {
+      const int64_t pos = strided ? ((int64_t)i * nblk + b) : ((int64_t)b * p + i);
+      out[(int64_t)tok * n + pos] = __float2half_rn(acc[c]);
+    }
+  }
+}
+
+// out[m][l] = in[m][idx ? idx[l] : l] * (scale ? scale[src] : 1) + (bias ? bias[l] : 0), one thread per 8 outputs
+// of one token: for a few tokens the grid is n/8 threads wide instead of one CTA per token row.
+__global__ void __launch_bounds__(128)
+gather_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int M, int n, const int32_t* __restrict__ idx,
+                     const float* __restrict__ scale, const __half* __restrict__ bias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n / 8) return;
+  const int l0 = c * 8;
+  int src[8];
+  float sc[8], bs[8];
+  if (idx) {                                               // parameters first: they do not depend on the previous kernel
+    const int4 a = *reinterpret_cast<const int4*>(idx + l0), b = *reinterpret_cast<const int4*>(idx + l0 + 4);
+    src[0] = a.x; src[1] = a.y; src[2] = a.z; src[3] = a.w; src[4] = b.x; src[5] = b.y; src[6] = b.z; src[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) src[i] = l0 + i;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = scale ? __ldg(scale + src[i]) : 1.f;
+    bs[i] = bias ? __half2float(__ldg(bias + l0 + i)) : 0.f;
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  for (int m = 0; m < M; ++m) {
+    __align__(16) __half v[8];
+    const __half* row = in + (int64_t)m * n;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __float2half_rn(fmaf(__half2float(__ldg(row + src[i])), sc[i], bs[i]));
+    *reinterpret_cast<uint4*>(out + (int64_t)m * n + l0) = *reinterpret_cast<const uint4*>(v);
+  }
+}
+
+int launch_pdl(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args);   // api.cu
+
+bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n) {
+  return M <= 8 && ps->p % 16 == 0 && ps->p >= 16 && (n % 4 == 0) && (((uintptr_t)ps->factors) & 7) == 0;
+}
+
+int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s) {
+  const int p = ps->p, ksteps = p / 16;
+  int kparts = 1;
+  while (kparts < FT_WARPS && ceil_div(ksteps, kparts) > FT_STEPS) kparts *= 2;
+  QUIP_CHECK_ARG(ceil_div(ksteps, kparts) <= FT_STEPS, "few-token pass: block size %d too large", p);
+  const int steps_per_part = ceil_div(ksteps, kparts);
+  const int64_t groups = (int64_t)ps->nblk * (p / 16);
+  const int per_cta = FT_WARPS / kparts;
+  const int Mi = (int)M, nblk = ps->nblk, strided = ps->strided, shared = ps->shared;
+  const __half* F = (const __half*)ps->factors;
+  void* args[] = {(void*)&in, (void*)&out, (void*)&F, (void*)&Mi, (void*)&n, (void*)&p, (void*)&nblk,
+                  (void*)&strided, (void*)&shared, (void*)&kparts, (void*)&steps_per_part};
+  if (int e = launch_pdl((const void*)pass_fewtok_kernel, dim3((unsigned)ceil_div(groups, per_cta)), dim3(FT_WARPS * 32), 0, s, args))
+    return e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QUIP_OK;
+}
+
+int gather_fewtok(const __half* in, __half* out, int64_t M, int n, const int32_t* idx, const float* scale,
+                  const __half* bias, cudaStream_t s) {
+  const int Mi = (int)M;
+  void* args[] = {(void*)&in, (void*)&out, (void*)&Mi, (void*)&n, (void*)&idx, (void*)&scale, (void*)&bias};
+  if (int e = launch_pdl((const void*)gather_fewtok_kernel, dim3((unsigned)ceil_div(n / 8, 128)), dim3(128), 0, s, args)) return e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QUIP_OK;
+}
+
+}  // namespace quip

@@ -25,8 +25,8 @@ GRAPH = False
 def timeit(fn, iters=50, warm=5):
     if ITERS:
         iters, warm = ITERS, 2
-    for _ in range(warm):
-        fn(0)
+    for w in range(max(warm, 8)):
+        fn(w)
     torch.cuda.synchronize()
     if GRAPH:
         # replay `iters` back-to-back launches from one CUDA graph: GPU time without the Python/ctypes launch cost
@@ -165,8 +165,8 @@ def main():
         res.append(bench_qgemm(32 * 11008, 4096, 16, 2, 1, 2, peaks)); print(res[-1], flush=True)
     if 'gemv' in what:
         lib = _lib.load()
-        keys = ('gemv', 'gv_int', 'gv_rbc', 'gv_persist')
-        defaults = dict(gemv=1, gv_int=1, gv_rbc=0, gv_persist=1)
+        keys = ('gemv', 'gv_int', 'gv_rbc', 'gv_persist', 'gv_tma', 'gv_cw')
+        defaults = dict(gemv=1, gv_int=1, gv_rbc=0, gv_persist=1, gv_tma=1, gv_cw=16)
 
         def run(N, K, M, bits, copies, **cfg):
             for k in keys:
@@ -174,16 +174,23 @@ def main():
             r = bench_qgemm(N, K, M, bits, 1, copies, peaks); r.update(cfg); res.append(r)
             print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()
                    if k not in ('TFLOPs', 'tensor_frac', 'kind', 'path')}, flush=True)
-        for (N, K) in shapes + [(32 * 11008, 4096)]:
+        if 'gemv2' in what:
+            for (N, K) in shapes + [(32 * 11008, 4096)]:
+                copies = max(2, int(300e6 // (N * K // 4)))
+                for M in (1, 4):
+                    for cw in (8, 16):
+                        for rbc in (1, 2):
+                            run(N, K, M, 2, copies, gv_cw=cw, gv_rbc=rbc)
+        for (N, K) in ([] if 'gemv2' in what else shapes + [(32 * 11008, 4096)]):
             copies = max(2, int(300e6 // (N * K // 4)))
             for M in (1, 2, 4, 8):
-                run(N, K, M, 2, copies, gemv=0)
                 for rbc in (1, 2):
-                    run(N, K, M, 2, copies, gv_int=1, gv_rbc=rbc)
-                    if M != 8:
-                        run(N, K, M, 2, copies, gv_int=0, gv_rbc=rbc)
+                    if M <= 5:
+                        run(N, K, M, 2, copies, gv_tma=1, gv_rbc=rbc)
+                        run(N, K, M, 2, copies, gv_tma=0, gv_rbc=rbc)
+                    run(N, K, M, 2, copies, gv_int=0, gv_rbc=rbc)
         for bits in (3, 4):
-            for g in (0, 1):
+            for g in ((1,) if 'gemv2' in what else (0, 1)):
                 run(11008, 4096, 1, bits, 8, gemv=g)
         for k in keys:
             lib.quip_config(k.encode(), defaults[k])
@@ -227,6 +234,16 @@ def main():
                 res.append(bench_pass(n, p, nblk, st, M)); print(res[-1], flush=True)
             res.append(bench_gather(4096, M)); print(res[-1], flush=True)
             res.append(bench_gather(11008, M)); print(res[-1], flush=True)
+    if 'decode' in what:
+        # one token through the three Llama-2-7B QuantLinear shapes, blocked butterflies + rescale (the as-run default)
+        lib = _lib.load()
+        for pdl in (1, 0):
+            lib.quip_config(b'pdl', pdl)
+            for (N, K) in shapes:
+                for M in (1, 4):
+                    r = bench_layer(N, K, M, 2, 'blocked', peaks, copies=4); r['pdl'] = pdl
+                    res.append(r); print(r, flush=True)
+        lib.quip_config(b'pdl', 1)
     if 'layer' in what:
         for (N, K) in shapes:
             for M in (1, 2048):
