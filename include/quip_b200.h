@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define QUIP_ABI_VERSION 1
+#define QUIP_ABI_VERSION 2
 
 enum {
   QUIP_OK = 0,
@@ -56,6 +56,12 @@ typedef struct {
   int32_t strided;
   int32_t shared;          /* 1: a single factor for every block (method.py:38-39, "noblock") */
   const void* factors;     /* fp16 [shared ? 1 : nblk][p][p], row-major */
+  const void* factors_frag;/* optional copy of the same factors in tensor-core fragment order, or NULL.  Only read by
+                              the one-kernel sides of the many-token forward (p in {32, 64}); without it those sides run
+                              as separate gather / pass kernels with the same result.  Word
+                              (((blk*(p/8) + nt)*(p/32) + j)*32 + lane)*4 + q  holds  F[blk][8nt + lane/4][k0], [k0+1]
+                              with k0 = 32j + 16(q/2) + 8(q%2) + 2(lane%4): one 128-bit load per lane is two k-steps
+                              of mma.m16n8k16 B fragments. */
 } QuipPass;
 
 /* One incoherence side: V acts on the K input features, U on the N outputs.
@@ -66,6 +72,9 @@ typedef struct {
   QuipPass pass[2];        /* execution order */
   const int32_t* idx;      /* gather index, length n, or NULL for identity:
                               V: layout[l] = x[idx[l]] ; U: y[j] = layout[idx[j]] */
+  const int32_t* inv_idx;  /* optional inverse of idx (inv_idx[idx[j]] = j), or NULL.  With it the few-token
+                              forward (M <= 8) writes the last U pass straight to y (one launch fewer); the
+                              result is the same without it. */
 } QuipSide;
 
 /* A packed linear layer  y = ((x * inv_scale) V^T) Q^T U + bias,

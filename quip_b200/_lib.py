@@ -13,13 +13,17 @@ QUIP_FLAG_SYMMETRIC = 1
 WS_HEADER_BYTES = 16 * 1024
 
 
+ABI_VERSION = 2
+
+
 class QuipPass(C.Structure):
     _fields_ = [('p', C.c_int32), ('nblk', C.c_int32), ('strided', C.c_int32), ('shared', C.c_int32),
-                ('factors', C.c_void_p)]
+                ('factors', C.c_void_p), ('factors_frag', C.c_void_p)]
 
 
 class QuipSide(C.Structure):
-    _fields_ = [('n', C.c_int32), ('npass', C.c_int32), ('passes', QuipPass * 2), ('idx', C.c_void_p)]
+    _fields_ = [('n', C.c_int32), ('npass', C.c_int32), ('passes', QuipPass * 2), ('idx', C.c_void_p),
+                ('inv_idx', C.c_void_p)]
 
 
 class QuipLinearDesc(C.Structure):
@@ -72,7 +76,7 @@ def load():
         for name, (res, args) in EXPORTS.items():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
-        if lib.quip_abi_version() != 1:
+        if lib.quip_abi_version() != ABI_VERSION:
             raise QuipError('libquip_b200.so ABI version mismatch')
         _lib = lib
     return _lib

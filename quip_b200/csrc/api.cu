@@ -38,11 +38,18 @@ int qgemm_ts(const QuipLinearDesc* d, const __half* x, const float* xsum, const 
              cudaStream_t s);
 
 extern int g_gather_rows, g_pass_min_tiles, g_fewtok;   // rot.cu
+bool side_fused_ok(const QuipSide* sd, int n);               // rot_side.cu
+int side_fused(const QuipSide* sd, const __half* in, __half* out, int64_t M, const int32_t* in_idx, const float* in_scale,
+               const int32_t* out_idx, const __half* out_bias, float* xsum, cudaStream_t s);
+bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n);   // rot_fewtok.cu
+int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
+                const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s);
 extern int g_gv_rbc, g_gv_persist, g_gv_int, g_gv_tma, g_gv_cw;  // qgemv.cu
 
 // tuning knobs (quip_config)
 static int g_use_tc2 = 0;        // route big-M contractions to the 2-CTA kernel
 static int g_use_ts = 0;         // route 2-bit big-M contractions to the TS-mode (A in TMEM) kernel
+static int g_side_fused = 1;     // many tokens: a whole side (gather + both passes [+ row sums]) in one kernel when the blocks allow
 static int g_pdl = 1;            // few-token kernels: programmatic dependent launch (weights prefetched under the previous kernel)
 static int g_use_gemv = 1;       // few-token contractions: whole-K qgemv kernel (0: the split-K kernel)
 
@@ -182,6 +189,7 @@ extern "C" int quip_config(const char* key, int value) {
   QUIP_CHECK_ARG(key != nullptr, "null key");
   if (!strcmp(key, "tc2")) { g_use_tc2 = value; return QUIP_OK; }
   if (!strcmp(key, "ts")) { g_use_ts = value; return QUIP_OK; }
+  if (!strcmp(key, "side_fused")) { g_side_fused = value; return QUIP_OK; }
   if (!strcmp(key, "pdl")) { g_pdl = value; return QUIP_OK; }
   if (!strcmp(key, "fewtok")) { g_fewtok = value; return QUIP_OK; }
   if (!strcmp(key, "gemv")) { g_use_gemv = value; return QUIP_OK; }
@@ -267,33 +275,59 @@ extern "C" int quip_qlinear_forward(const QuipLinearDesc* d, const void* x_, voi
 
   // ---- K side: x2 = passes( (x * inv_scale)[idx] ) ----
   const __half* cur = x;
-  if (d->V.idx || d->inv_scale) {
-    if (int e = quip_gather(cur, bufA, M, K, d->V.n ? d->V.idx : nullptr, d->inv_scale, nullptr, stream)) return e;
+  const int vpass = d->V.n ? d->V.npass : 0;
+  const bool need_xsum = !(d->flags & QUIP_FLAG_SYMMETRIC) && M > SKINNY_MAX_M;
+  bool have_xsum = false;
+  if (g_side_fused && M > 8 && vpass == 2 && side_fused_ok(&d->V, K)) {
+    // many tokens: the whole side in one kernel, 16 token rows resident in shared memory
+    if (int e = side_fused(&d->V, x, bufA, M, d->V.idx, d->inv_scale, nullptr, nullptr, need_xsum ? xsum : nullptr, s)) return e;
     cur = bufA;
-  }
-  for (int i = 0; i < (d->V.n ? d->V.npass : 0); ++i) {
-    __half* dst = (cur == bufA) ? bufB : bufA;
-    if (int e = quip_rot_pass(&d->V.pass[i], cur, dst, M, K, 0, stream)) return e;
-    cur = dst;
+    have_xsum = need_xsum;
+  } else {
+    // few tokens: the gather (index + 1/s) rides on the first pass's operand load
+    // (small blocks only: a 688-wide block is shared by 21 CTAs, which would each repeat the indexed reads)
+    const bool fuse_in = g_fewtok && M <= 8 && vpass > 0 && d->V.pass[0].p <= 128 && pass_fewtok_ok(&d->V.pass[0], M, K);
+    if ((d->V.idx || d->inv_scale) && !fuse_in) {
+      if (int e = quip_gather(cur, bufA, M, K, d->V.n ? d->V.idx : nullptr, d->inv_scale, nullptr, stream)) return e;
+      cur = bufA;
+    }
+    for (int i = 0; i < vpass; ++i) {
+      __half* dst = (cur == bufA) ? bufB : bufA;
+      if (i == 0 && fuse_in) {
+        if (int e = pass_fewtok(&d->V.pass[0], cur, dst, M, K, d->V.idx, d->inv_scale, nullptr, nullptr, s)) return e;
+      } else if (int e = quip_rot_pass(&d->V.pass[i], cur, dst, M, K, 0, stream)) {
+        return e;
+      }
+      cur = dst;
+    }
   }
   const __half* x2 = cur;
 
   // ---- contraction with the packed matrix ----
   const bool u_on = side_on(d->U);
-  const bool need_xsum = !(d->flags & QUIP_FLAG_SYMMETRIC) && M > SKINNY_MAX_M;
-  if (need_xsum)
+  if (need_xsum && !have_xsum)
     if (int e = quip_rowsum(x2, xsum, M, K, stream)) return e;
   __half* zdst = u_on ? zbuf : y;
   if (int e = run_qgemm(d, x2, xsum, u_on ? nullptr : (const __half*)d->bias, zdst, M, 0, ws, p, s)) return e;
   if (!u_on) return QUIP_OK;
 
   // ---- N side: y = passes(z)[idx] + bias ----
+  if (g_side_fused && M > 8 && d->U.npass == 2 && side_fused_ok(&d->U, N))
+    return side_fused(&d->U, zbuf, y, M, nullptr, nullptr, d->U.idx, (const __half*)d->bias, nullptr, s);
   const __half* zc = zbuf;
   const int np = d->U.npass;
-  const bool tail_gather = d->U.idx || d->bias;
+  bool tail_gather = d->U.idx || d->bias;
+  // few tokens: the last pass scatters through the inverse index and adds the bias itself
+  const bool fuse_out = tail_gather && g_fewtok && M <= 8 && np > 0 && (!d->U.idx || d->U.inv_idx) &&
+                        pass_fewtok_ok(&d->U.pass[np - 1], M, N);
+  if (fuse_out) tail_gather = false;
   for (int i = 0; i < np; ++i) {
     __half* dst = (i == np - 1 && !tail_gather) ? y : ((zc == zbuf) ? bufC : zbuf);
-    if (int e = quip_rot_pass(&d->U.pass[i], zc, dst, M, N, 0, stream)) return e;
+    if (i == np - 1 && fuse_out) {
+      if (int e = pass_fewtok(&d->U.pass[i], zc, dst, M, N, nullptr, nullptr, d->U.inv_idx, (const __half*)d->bias, s)) return e;
+    } else if (int e = quip_rot_pass(&d->U.pass[i], zc, dst, M, N, 0, stream)) {
+      return e;
+    }
     zc = dst;
   }
   if (tail_gather) return quip_gather(zc, y, M, N, d->U.idx, nullptr, d->bias, stream);

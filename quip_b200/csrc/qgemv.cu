@@ -620,8 +620,8 @@ qgemv_i8_tma_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x
   int8_t* limbs = reinterpret_cast<int8_t*>(ring + (size_t)NS * STAGE_BYTES);              // [ncol][lld]
   int* red = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(limbs) + (((size_t)ncol * lld + 15) & ~(size_t)15));
   float* tokf = reinterpret_cast<float*>(red + 2 * W * COLS * RLD);                        // [8][2]: s_m, S_m
-  float* wred = tokf + 16;                                                                 // [W][2]
-  uint64_t* full = reinterpret_cast<uint64_t*>(wred + 2 * W);                              // [NS]
+  float* wred = tokf + 16;                                                                 // [2 * 5 tokens][W]
+  uint64_t* full = reinterpret_cast<uint64_t*>(wred + 10 * W);                             // [NS]
   uint64_t* empty = full + NS;                                                             // [NS]
   uint64_t* red_full = empty + NS;                                                         // [2]
   uint64_t* red_empty = red_full + 2;                                                      // [2]
@@ -705,62 +705,87 @@ qgemv_i8_tma_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x
 
   // ===================== consumer warps =====================
   // ---- tokens -> three signed bytes each, once per CTA (the ring fills meanwhile) ----
+  // one sweep for the maxima and sums of all tokens (a single barrier), one sweep to quantise
   const int cpr = K >> 3;
-  const int ctid = tid;                                   // consumers are threads 0 .. 255
-  for (int tok = 0; tok < M; ++tok) {
-    const uint4* src = reinterpret_cast<const uint4*>(x + (int64_t)tok * K);
-    float amax = 0.f, sum = 0.f;
+  const int ctid = tid;                                   // consumers are threads 0 .. W*32-1
+  constexpr int MAXTOK = 5;
+  {
+    float amax[MAXTOK], sum[MAXTOK];
+#pragma unroll
+    for (int tok = 0; tok < MAXTOK; ++tok) { amax[tok] = 0.f; sum[tok] = 0.f; }
     for (int c = ctid; c < cpr; c += W * 32) {
-      const uint4 v = src[c];
-      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h2[i]);
-        amax = fmaxf(amax, fmaxf(fabsf(f.x), fabsf(f.y)));
-        sum += f.x + f.y;
+      for (int tok = 0; tok < MAXTOK; ++tok) {
+        if (tok < M) {
+          const uint4 v = *reinterpret_cast<const uint4*>(x + (int64_t)tok * K + 8 * c);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h2[i]);
+            amax[tok] = fmaxf(amax[tok], fmaxf(fabsf(f.x), fabsf(f.y)));
+            sum[tok] += f.x + f.y;
+          }
+        }
       }
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-      sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    }
-    if (lane == 0) { wred[2 * warp] = amax; wred[2 * warp + 1] = sum; }
-    consumer_sync<CW>();
-    amax = 0.f; sum = 0.f;
+    for (int tok = 0; tok < MAXTOK; ++tok) {
+      if (tok < M) {
 #pragma unroll
-    for (int w = 0; w < W; ++w) { amax = fmaxf(amax, wred[2 * w]); sum += wred[2 * w + 1]; }
-    const float inv = amax > 0.f ? GV_QMAX / amax : 0.f;
-    if (ctid == 0) { tokf[2 * tok] = amax / GV_QMAX; tokf[2 * tok + 1] = sum; }
-    for (int c = ctid; c < cpr; c += W * 32) {
-      const uint4 v = src[c];
-      const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-      int qv[8];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float2 f = __half22float2(h2[i]);
-        qv[2 * i] = __float2int_rn(f.x * inv);
-        qv[2 * i + 1] = __float2int_rn(f.y * inv);
+        for (int o = 16; o; o >>= 1) {
+          amax[tok] = fmaxf(amax[tok], __shfl_xor_sync(0xffffffffu, amax[tok], o));
+          sum[tok] += __shfl_xor_sync(0xffffffffu, sum[tok], o);
+        }
+        if (lane == 0) { wred[(2 * tok) * W + warp] = amax[tok]; wred[(2 * tok + 1) * W + warp] = sum[tok]; }
       }
-      uint32_t lb[GV_LIMBS][2] = {};
-#pragma unroll
-      for (int sidx = 0; sidx < 8; ++sidx) {
-        constexpr int PI[8] = {0, 2, 1, 3, 4, 6, 5, 7};
-        int v0 = qv[PI[sidx]];
-        const int lo = (int)(int8_t)(v0 & 0xFF);
-        v0 = (v0 - lo) >> 8;
-        const int mid = (int)(int8_t)(v0 & 0xFF);
-        const int hi = (v0 - mid) >> 8;
-        lb[0][sidx >> 2] |= (uint32_t)(hi & 0xFF) << (8 * (sidx & 3));
-        lb[1][sidx >> 2] |= (uint32_t)(mid & 0xFF) << (8 * (sidx & 3));
-        lb[2][sidx >> 2] |= (uint32_t)(lo & 0xFF) << (8 * (sidx & 3));
-      }
-#pragma unroll
-      for (int l = 0; l < GV_LIMBS; ++l)
-        *reinterpret_cast<uint2*>(limbs + (size_t)(GV_LIMBS * tok + l) * lld + 8 * c) = make_uint2(lb[l][0], lb[l][1]);
     }
-    consumer_sync<CW>();
   }
+  consumer_sync<CW>();
+  float inv[MAXTOK];
+#pragma unroll
+  for (int tok = 0; tok < MAXTOK; ++tok) {
+    inv[tok] = 0.f;
+    if (tok < M) {
+      float amax = 0.f, sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < W; ++w) { amax = fmaxf(amax, wred[(2 * tok) * W + w]); sum += wred[(2 * tok + 1) * W + w]; }
+      inv[tok] = amax > 0.f ? GV_QMAX / amax : 0.f;
+      if (ctid == 0) { tokf[2 * tok] = amax / GV_QMAX; tokf[2 * tok + 1] = sum; }
+    }
+  }
+  for (int c = ctid; c < cpr; c += W * 32) {
+#pragma unroll
+    for (int tok = 0; tok < MAXTOK; ++tok) {
+      if (tok < M) {
+        const uint4 v = *reinterpret_cast<const uint4*>(x + (int64_t)tok * K + 8 * c);   // second read hits L1/L2
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+        int qv[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h2[i]);
+          qv[2 * i] = __float2int_rn(f.x * inv[tok]);
+          qv[2 * i + 1] = __float2int_rn(f.y * inv[tok]);
+        }
+        uint32_t lb[GV_LIMBS][2] = {};
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) {
+          constexpr int PI[8] = {0, 2, 1, 3, 4, 6, 5, 7};
+          int v0 = qv[PI[sidx]];
+          const int lo = (int)(int8_t)(v0 & 0xFF);
+          v0 = (v0 - lo) >> 8;
+          const int mid = (int)(int8_t)(v0 & 0xFF);
+          const int hi = (v0 - mid) >> 8;
+          lb[0][sidx >> 2] |= (uint32_t)(hi & 0xFF) << (8 * (sidx & 3));
+          lb[1][sidx >> 2] |= (uint32_t)(mid & 0xFF) << (8 * (sidx & 3));
+          lb[2][sidx >> 2] |= (uint32_t)(lo & 0xFF) << (8 * (sidx & 3));
+        }
+#pragma unroll
+        for (int l = 0; l < GV_LIMBS; ++l)
+          *reinterpret_cast<uint2*>(limbs + (size_t)(GV_LIMBS * tok + l) * lld + 8 * c) = make_uint2(lb[l][0], lb[l][1]);
+      }
+    }
+  }
+  consumer_sync<CW>();
 
   int slot = 0;                                           // ring position, advanced like the producer's
   uint32_t ph = 0, tcount = 0;
@@ -923,7 +948,7 @@ static int launch_gv_i8_tma(const QuipLinearDesc* d, const __half* x, const __ha
   constexpr int COLS = 8 * NT8, ROWS = 16 * RBC, RLD = ROWS + 4;
   constexpr size_t STAGE_BYTES = (size_t)GT_STAGE_SB * sb_words(BITS) * 4;
   const size_t limb_bytes = ((size_t)GV_LIMBS * M * (d->K + 32) + 15) & ~(size_t)15;
-  const size_t fixed = limb_bytes + (size_t)(2 * CW * COLS * RLD) * sizeof(int) + (size_t)(16 + 2 * CW) * sizeof(float);
+  const size_t fixed = limb_bytes + (size_t)(2 * CW * COLS * RLD) * sizeof(int) + (size_t)(16 + 10 * CW) * sizeof(float);
   const size_t budget = 227 * 1024 - 256;
   int ns = fixed + 64 < budget ? (int)((budget - fixed - 64) / (STAGE_BYTES + 16)) : 0;
   if (ns > 12) ns = 12;
@@ -952,7 +977,7 @@ static int launch_gv_i8_tma(const QuipLinearDesc* d, const __half* x, const __ha
 // does the bulk-copy kernel have room for at least a minimal ring next to the token bytes?
 static bool gv_tma_fits(int K, int M, int bits, int nt8, int rbc, int cw) {
   const size_t stage = (size_t)GT_STAGE_SB * sb_words(bits) * 4;
-  const size_t fixed = (size_t)GV_LIMBS * M * (K + 32) + (size_t)(2 * cw * 8 * nt8 * (16 * rbc + 4)) * 4 + 512;
+  const size_t fixed = (size_t)GV_LIMBS * M * (K + 32) + (size_t)(2 * cw * 8 * nt8 * (16 * rbc + 4)) * 4 + 1024;
   return fixed + (size_t)(2 * rbc + 2) * (stage + 16) <= (size_t)227 * 1024 - 256;
 }
 

@@ -399,7 +399,8 @@ static int launch_gather(const __half* in, __half* out, int64_t M, int n, const 
 
 namespace quip {
 bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n);
-int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s);
+int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
+                const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s);
 int gather_fewtok(const __half* in, __half* out, int64_t M, int n, const int32_t* idx, const float* scale,
                   const __half* bias, cudaStream_t s);
 int pass_big_tc(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s);
@@ -459,7 +460,8 @@ extern "C" int quip_rot_pass(const QuipPass* ps, const void* in_, void* out_, in
   const __half* in = (const __half*)in_;
   __half* out = (__half*)out_;
   const int p = ps->p;
-  if (impl == 0 && g_fewtok && pass_fewtok_ok(ps, M, n)) return pass_fewtok(ps, in, out, M, n, s);
+  if (impl == 0 && g_fewtok && pass_fewtok_ok(ps, M, n))
+    return pass_fewtok(ps, in, out, M, n, nullptr, nullptr, nullptr, nullptr, s);
   bool small_ok = p <= 64;
   bool big_ok = p > 64 && !ps->strided && p % 8 == 0 && n % 8 == 0;
   if (impl != 1 && small_ok) {

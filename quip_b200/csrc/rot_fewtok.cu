@@ -20,17 +20,30 @@ namespace quip {
 constexpr int FT_WARPS = 8;
 constexpr int FT_STEPS = 12;           // k16 steps per task: 12 x (2 x 8 B) per lane in flight
 
+constexpr int FT_XPT = 6;              // input elements staged per thread (covers 2 blocks of 688)
+
+// Optional fusions (the few-token forward of api.cu uses both, saving two launches per QuantLinear):
+//   in_idx / in_scale : the pass reads  in[m][in_idx[pos]] * in_scale[in_idx[pos]]  instead of in[m][pos]
+//                       (the K-side gather + 1/s of quip_gather, rounded to fp16 exactly as it rounds)
+//   out_inv / out_bias: the pass writes out[m][out_inv[pos]] = value + out_bias[out_inv[pos]]
+//                       (the N-side gather y[j] = layout[idx[j]] + bias[j], out_inv = idx^-1)
 __global__ void __launch_bounds__(FT_WARPS * 32)
 pass_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, const __half* __restrict__ F, int M, int n,
-                   int p, int nblk, int strided, int shared, int kparts, int steps_per_part) {
+                   int p, int nblk, int strided, int shared, int kparts, int steps_per_part,
+                   const int32_t* __restrict__ in_idx, const float* __restrict__ in_scale,
+                   const int32_t* __restrict__ out_inv, const __half* __restrict__ out_bias, int nb_cta) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[FT_WARPS][16][9];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  __half* xs = reinterpret_cast<__half*>(smem_raw);        // [M][xld]: the input blocks this CTA multiplies
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int rtiles = p >> 4;                               // 16-row tiles per block
   const int groups_per_cta = FT_WARPS / kparts;            // (block, row tile) pairs per CTA
   const int grp = warp / kparts, part = warp % kparts;
-  const int64_t task = (int64_t)blockIdx.x * groups_per_cta + grp;
+  const int64_t task0 = (int64_t)blockIdx.x * groups_per_cta, task = task0 + grp;
   const bool live = task < (int64_t)nblk * rtiles;
   const int b = live ? (int)(task / rtiles) : 0, rt = live ? (int)(task % rtiles) : 0;
+  const int b_first = (int)(task0 / rtiles);
+  const int xld = nb_cta * p + 16;
   const int ksteps = p >> 4;
   const int s0 = part * steps_per_part, s1 = min(ksteps, s0 + steps_per_part);
 
@@ -46,27 +59,69 @@ pass_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
       a_hi[s] = ldg_nc_v2(frow + (int64_t)8 * p + (s0 + s) * 16);
     }
   }
+  // ---- where this CTA's inputs and outputs live: index vectors are parameters too ----
+  // plain contiguous input (no index, no scale): 8-byte copies after the wait; otherwise element by element
+  const bool vec_in = !strided && !in_idx && !in_scale;
+  const int b_last = min(nblk - 1, (int)((task0 + groups_per_cta - 1) / rtiles));
+  int src[FT_XPT];
+  float ssc[FT_XPT];
+#pragma unroll
+  for (int i = 0; i < FT_XPT; ++i) {
+    const int e = tid + i * FT_WARPS * 32;
+    src[i] = -1;
+    ssc[i] = 1.f;
+    if (!vec_in && e < nb_cta * p) {
+      const int bl = e / p, j = e - bl * p, bb = b_first + bl;
+      if (bb <= b_last) {
+        const int pos = strided ? (j * nblk + bb) : (bb * p + j);
+        src[i] = in_idx ? __ldg(in_idx + pos) : pos;
+        if (in_scale) ssc[i] = __ldg(in_scale + src[i]);
+      }
+    }
+  }
+  int dst[2];
+  float dbias[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int i = rt * 16 + g + 8 * h;
+    const int pos = strided ? (i * nblk + b) : (b * p + i);
+    dst[h] = (live && out_inv) ? __ldg(out_inv + pos) : pos;
+    dbias[h] = (live && out_bias) ? __half2float(__ldg(out_bias + dst[h])) : 0.f;
+  }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // ---- tokens: lane (g, t) needs x[token g][k = 16 s + 4 t .. +3]; columns >= M re-read the last token ----
-  const __half* xrow = in + (int64_t)min(g, M - 1) * n;
+  // ---- stage the tokens of this CTA's blocks ----
+  if (vec_in) {
+    const int nq = (b_last - b_first + 1) * p / 4;         // 8-byte groups per token (p % 16 == 0)
+    for (int e = tid; e < nq * M; e += FT_WARPS * 32) {
+      const int m = e / nq, qd = e - m * nq;
+      *reinterpret_cast<uint2*>(xs + m * xld + 4 * qd) =
+          *reinterpret_cast<const uint2*>(in + (int64_t)m * n + (int64_t)b_first * p + 4 * qd);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < FT_XPT; ++i) {
+      const int e = tid + i * FT_WARPS * 32;
+      if (src[i] >= 0) {
+#pragma unroll 4
+        for (int m = 0; m < M; ++m) {
+          const float v = __half2float(__ldg(in + (int64_t)m * n + src[i]));
+          xs[m * xld + e] = in_scale ? __float2half_rn(v * ssc[i]) : __float2half_rn(v);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- lane (g, t) needs x[token g][k = 16 s + 4 t .. +3]; columns >= M re-read the last token ----
+  const __half* xrow = xs + min(g, M - 1) * xld + (b - b_first) * p + 4 * t;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int s = 0; s < FT_STEPS; ++s) {
-    if (s0 + s < s1) {
-      const int j = (s0 + s) * 16 + 4 * t;
-      uint32_t bfrag[2];
-      if (strided) {
-        const __half* xp = xrow + (int64_t)j * nblk + b;
-        const uint32_t h0 = __half_as_ushort(__ldg(xp)), h1 = __half_as_ushort(__ldg(xp + nblk));
-        const uint32_t h2 = __half_as_ushort(__ldg(xp + 2 * (int64_t)nblk)), h3 = __half_as_ushort(__ldg(xp + 3 * (int64_t)nblk));
-        bfrag[0] = h0 | (h1 << 16);
-        bfrag[1] = h2 | (h3 << 16);
-      } else {
-        const uint2 v = *reinterpret_cast<const uint2*>(xrow + (int64_t)b * p + j);
-        bfrag[0] = v.x; bfrag[1] = v.y;
-      }
+    if (live && s0 + s < s1) {
+      const uint2 v = *reinterpret_cast<const uint2*>(xrow + (s0 + s) * 16);
+      const uint32_t bfrag[2] = {v.x, v.y};
       // k relabelled so that a lane's four consecutive k are MMA slots (2t, 2t+1, 2t+8, 2t+9) on both operands
       const uint32_t a[4] = {a_lo[s].x, a_hi[s].x, a_lo[s].y, a_hi[s].y};
       mma16816(acc, a, bfrag);
@@ -89,10 +144,11 @@ pass_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
   if (!live) return;
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    const int tok = 2 * t + (c & 1), i = rt * 16 + g + 8 * (c >> 1);
+    const int tok = 2 * t + (c & 1), h = c >> 1;
     if (tok < M) {
-      const int64_t pos = strided ? ((int64_t)i * nblk + b) : ((int64_t)b * p + i);
-      out[(int64_t)tok * n + pos] = __float2half_rn(acc[c]);
+      // fused bias: the pass result is rounded to fp16 first, as the stand-alone gather would read it
+      const float v = out_bias ? __half2float(__float2half_rn(acc[c])) + dbias[h] : acc[c];
+      out[(int64_t)tok * n + dst[h]] = __float2half_rn(v);
     }
   }
 }
@@ -136,19 +192,26 @@ bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n) {
   return M <= 8 && ps->p % 16 == 0 && ps->p >= 16 && (n % 4 == 0) && (((uintptr_t)ps->factors) & 7) == 0;
 }
 
-int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, cudaStream_t s) {
+int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
+                const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s) {
   const int p = ps->p, ksteps = p / 16;
   int kparts = 1;
   while (kparts < FT_WARPS && ceil_div(ksteps, kparts) > FT_STEPS) kparts *= 2;
   QUIP_CHECK_ARG(ceil_div(ksteps, kparts) <= FT_STEPS, "few-token pass: block size %d too large", p);
   const int steps_per_part = ceil_div(ksteps, kparts);
-  const int64_t groups = (int64_t)ps->nblk * (p / 16);
+  const int rtiles = p / 16;
+  const int64_t groups = (int64_t)ps->nblk * rtiles;
   const int per_cta = FT_WARPS / kparts;
+  int nb_cta = (per_cta + rtiles - 1) / rtiles + ((per_cta % rtiles) && (rtiles % per_cta) ? 1 : 0);   // blocks a CTA can touch
+  if (nb_cta > ps->nblk) nb_cta = ps->nblk;
+  QUIP_CHECK_ARG(nb_cta * p <= FT_XPT * FT_WARPS * 32, "few-token pass: %d blocks of %d per CTA exceed the staging budget", nb_cta, p);
+  const size_t smem = (size_t)M * (nb_cta * p + 16) * sizeof(__half);
   const int Mi = (int)M, nblk = ps->nblk, strided = ps->strided, shared = ps->shared;
   const __half* F = (const __half*)ps->factors;
   void* args[] = {(void*)&in, (void*)&out, (void*)&F, (void*)&Mi, (void*)&n, (void*)&p, (void*)&nblk,
-                  (void*)&strided, (void*)&shared, (void*)&kparts, (void*)&steps_per_part};
-  if (int e = launch_pdl((const void*)pass_fewtok_kernel, dim3((unsigned)ceil_div(groups, per_cta)), dim3(FT_WARPS * 32), 0, s, args))
+                  (void*)&strided, (void*)&shared, (void*)&kparts, (void*)&steps_per_part, (void*)&in_idx,
+                  (void*)&in_scale, (void*)&out_inv, (void*)&out_bias, (void*)&nb_cta};
+  if (int e = launch_pdl((const void*)pass_fewtok_kernel, dim3((unsigned)ceil_div(groups, per_cta)), dim3(FT_WARPS * 32), smem, s, args))
     return e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QUIP_OK;

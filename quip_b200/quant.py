@@ -178,6 +178,14 @@ def _native_fields(N, K, bits, device):
             (base + 128 + lane * 2 + ch // 2, 8 * (ch % 2) + j + 16 * e, 0, 1)]
 
 
+def fragment_order(f: torch.Tensor) -> torch.Tensor:
+    """Block-diagonal factors (nblk, p, p) fp16, row-major  ->  mma.m16n8k16 B-fragment order (QuipPass.factors_frag):
+    [blk][n-tile][k/32][lane = 4g+t][q][pair], element (i = 8nt+g, k = 32j + 16(q//2) + 8(q%2) + 2t + pair)."""
+    nblk, p, _ = f.shape
+    v = f.reshape(nblk, p // 8, 8, p // 32, 2, 2, 4, 2)          # blk, nt, g, j, q//2, q%2, t, pair
+    return v.permute(0, 1, 3, 2, 6, 4, 5, 7).contiguous()        # blk, nt, j, g, t, q//2, q%2, pair
+
+
 def pack_codes(codes: torch.Tensor, bits: int) -> torch.Tensor:
     """codes (N, K) uint8 -> native packed int32 words.  On CUDA tensors this is quip_pack_codes (the GPU
     packer the reference leaves as a TODO, opt.py:302); on CPU tensors the same bit layout is built with
@@ -445,13 +453,29 @@ class QuantLinear(nn.Module):
             s.passes[i].p, s.passes[i].nblk, s.passes[i].strided = d['p'], d['nblk'], d['strided']
             s.passes[i].shared = int(f.shape[0] == 1 and d['nblk'] > 1)
             s.passes[i].factors = f.data_ptr()
+            s.passes[i].factors_frag = None
+            if d['p'] in (32, 64) and n <= 4096:
+                # tensor-core fragment order for the one-kernel sides (include/quip_b200.h): derived, not a checkpoint buffer
+                frag = fragment_order(f)
+                self._frag_keep[f'{side}{i}'] = frag
+                s.passes[i].factors_frag = frag.data_ptr()
         identity = bool(self.meta_host[3 if side == 'v' else 4])
         s.idx = None if identity else getattr(self, f'{side}_idx').data_ptr()
+        s.inv_idx = None
+        if side == 'u' and not identity:
+            # inverse of the output gather, derived once (not a checkpoint buffer): lets the few-token forward
+            # scatter the last U pass straight into y
+            idx = self.u_idx
+            inv = torch.empty_like(idx)
+            inv[idx.long()] = torch.arange(idx.numel(), dtype=idx.dtype, device=idx.device)
+            self._u_inv = inv
+            s.inv_idx = inv.data_ptr()
         return s
 
     def _descriptor(self):
         if self._desc is None:
             self.meta_host = self.meta.tolist()
+            self._frag_keep = {}
             d = _lib.QuipLinearDesc()
             d.K, d.N, d.bits = self.infeatures, self.outfeatures, self.bits
             d.flags = _lib.QUIP_FLAG_SYMMETRIC if self.meta_host[1] else 0

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f'{name} declared in include/quip_b200.h but not exported'
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
-    assert lib.quip_abi_version() == 1
+    assert lib.quip_abi_version() == _lib.ABI_VERSION == 2
     assert lib.quip_packed_words(16, 128, 2) == 128
     assert lib.quip_packed_words(16, 128, 3) == 192
     assert lib.quip_packed_words(16, 100, 2) == 0          # bad shape -> 0

@@ -244,6 +244,13 @@ def main():
                     r = bench_layer(N, K, M, 2, 'blocked', peaks, copies=4); r['pdl'] = pdl
                     res.append(r); print(r, flush=True)
         lib.quip_config(b'pdl', 1)
+    if 'side' in what:
+        lib = _lib.load()
+        for sf in (0, 1):
+            lib.quip_config(b'side_fused', sf)
+            for (N, K) in [(4096, 4096), (11008, 4096), (4096, 11008)]:
+                r = bench_layer(N, K, 2048, 2, 'blocked', peaks); r['side_fused'] = sf; res.append(r); print(r, flush=True)
+        lib.quip_config(b'side_fused', 1)
     if 'layer' in what:
         for (N, K) in shapes:
             for M in (1, 2048):
