@@ -44,7 +44,7 @@ int side_fused(const QuipSide* sd, const __half* in, __half* out, int64_t M, con
 bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n);   // rot_fewtok.cu
 int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
                 const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s);
-extern int g_gv_rbc, g_gv_persist, g_gv_int, g_gv_tma, g_gv_cw;  // qgemv.cu
+extern int g_gv_rbc, g_gv_persist, g_gv_int, g_gv_tma, g_gv_cw, g_gv_stream;  // qgemv.cu
 
 // tuning knobs (quip_config)
 static int g_use_tc2 = 0;        // route big-M contractions to the 2-CTA kernel
@@ -194,6 +194,7 @@ extern "C" int quip_config(const char* key, int value) {
   if (!strcmp(key, "fewtok")) { g_fewtok = value; return QUIP_OK; }
   if (!strcmp(key, "gemv")) { g_use_gemv = value; return QUIP_OK; }
   if (!strcmp(key, "gv_rbc")) { g_gv_rbc = value; return QUIP_OK; }
+  if (!strcmp(key, "gv_stream")) { g_gv_stream = value; return QUIP_OK; }
   if (!strcmp(key, "gv_cw")) { g_gv_cw = value; return QUIP_OK; }
   if (!strcmp(key, "gv_tma")) { g_gv_tma = value; return QUIP_OK; }
   if (!strcmp(key, "gv_int")) { g_gv_int = value; return QUIP_OK; }

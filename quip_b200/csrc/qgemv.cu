@@ -41,6 +41,7 @@ int g_gv_rbc = 0;                      // quip_config("gv_rbc", r): row blocks p
 int g_gv_int = 1;                      // quip_config("gv_int", 0): fp16 tensor path for every token count
 int g_gv_tma = 1;                      // quip_config("gv_tma", 0): register-ring variant of the int8 path
 int g_gv_cw = 16;                      // quip_config("gv_cw", 8|16): consumer warps of the bulk-copy kernel
+int g_gv_stream = 32;                  // quip_config("gv_stream", r): streaming kernel when N/16 >= r * SMs (0: never)
 int g_gv_persist = 1;                  // quip_config("gv_persist", 0): one CTA per row tile instead of a persistent grid
 
 template <int BITS>
@@ -599,6 +600,95 @@ __device__ __forceinline__ void gv_lds(const uint32_t* sb, int lane, GvRegs<BITS
   }
 }
 
+// Tokens -> three balanced signed bytes of round(x * 2^22 / amax) each, in slot order, once per CTA; also s_m and the
+// plain row sum S_m (tokf).  Called by the W consumer warps only (named barrier 1).
+template <int W>
+__device__ __forceinline__ void gv_quantize_tokens(const __half* __restrict__ x, int M, int K, int8_t* limbs, int lld,
+                                                   float* tokf, float* wred, int ctid, int warp, int lane) {
+  const int cpr = K >> 3;
+  // ---- tokens -> three signed bytes each, once per CTA (the ring fills meanwhile) ----
+  // one sweep for the maxima and sums of all tokens (a single barrier), one sweep to quantise
+  constexpr int MAXTOK = 5;
+  {
+    float amax[MAXTOK], sum[MAXTOK];
+#pragma unroll
+    for (int tok = 0; tok < MAXTOK; ++tok) { amax[tok] = 0.f; sum[tok] = 0.f; }
+    for (int c = ctid; c < cpr; c += W * 32) {
+#pragma unroll
+      for (int tok = 0; tok < MAXTOK; ++tok) {
+        if (tok < M) {
+          const uint4 v = *reinterpret_cast<const uint4*>(x + (int64_t)tok * K + 8 * c);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(h2[i]);
+            amax[tok] = fmaxf(amax[tok], fmaxf(fabsf(f.x), fabsf(f.y)));
+            sum[tok] += f.x + f.y;
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int tok = 0; tok < MAXTOK; ++tok) {
+      if (tok < M) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+          amax[tok] = fmaxf(amax[tok], __shfl_xor_sync(0xffffffffu, amax[tok], o));
+          sum[tok] += __shfl_xor_sync(0xffffffffu, sum[tok], o);
+        }
+        if (lane == 0) { wred[(2 * tok) * W + warp] = amax[tok]; wred[(2 * tok + 1) * W + warp] = sum[tok]; }
+      }
+    }
+  }
+  consumer_sync<W>();
+  float inv[MAXTOK];
+#pragma unroll
+  for (int tok = 0; tok < MAXTOK; ++tok) {
+    inv[tok] = 0.f;
+    if (tok < M) {
+      float amax = 0.f, sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < W; ++w) { amax = fmaxf(amax, wred[(2 * tok) * W + w]); sum += wred[(2 * tok + 1) * W + w]; }
+      inv[tok] = amax > 0.f ? GV_QMAX / amax : 0.f;
+      if (ctid == 0) { tokf[2 * tok] = amax / GV_QMAX; tokf[2 * tok + 1] = sum; }
+    }
+  }
+  for (int c = ctid; c < cpr; c += W * 32) {
+#pragma unroll
+    for (int tok = 0; tok < MAXTOK; ++tok) {
+      if (tok < M) {
+        const uint4 v = *reinterpret_cast<const uint4*>(x + (int64_t)tok * K + 8 * c);   // second read hits L1/L2
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+        int qv[8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(h2[i]);
+          qv[2 * i] = __float2int_rn(f.x * inv[tok]);
+          qv[2 * i + 1] = __float2int_rn(f.y * inv[tok]);
+        }
+        uint32_t lb[GV_LIMBS][2] = {};
+#pragma unroll
+        for (int sidx = 0; sidx < 8; ++sidx) {
+          constexpr int PI[8] = {0, 2, 1, 3, 4, 6, 5, 7};
+          int v0 = qv[PI[sidx]];
+          const int lo = (int)(int8_t)(v0 & 0xFF);
+          v0 = (v0 - lo) >> 8;
+          const int mid = (int)(int8_t)(v0 & 0xFF);
+          const int hi = (v0 - mid) >> 8;
+          lb[0][sidx >> 2] |= (uint32_t)(hi & 0xFF) << (8 * (sidx & 3));
+          lb[1][sidx >> 2] |= (uint32_t)(mid & 0xFF) << (8 * (sidx & 3));
+          lb[2][sidx >> 2] |= (uint32_t)(lo & 0xFF) << (8 * (sidx & 3));
+        }
+#pragma unroll
+        for (int l = 0; l < GV_LIMBS; ++l)
+          *reinterpret_cast<uint2*>(limbs + (size_t)(GV_LIMBS * tok + l) * lld + 8 * c) = make_uint2(lb[l][0], lb[l][1]);
+      }
+    }
+  }
+  consumer_sync<W>();
+
+}
+
 template <int BITS, int NT8, int RBC, int CW>
 __global__ void __launch_bounds__(gt_threads(CW))
 qgemv_i8_tma_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x, const float* __restrict__ scales,
@@ -705,87 +795,7 @@ qgemv_i8_tma_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x
 
   // ===================== consumer warps =====================
   // ---- tokens -> three signed bytes each, once per CTA (the ring fills meanwhile) ----
-  // one sweep for the maxima and sums of all tokens (a single barrier), one sweep to quantise
-  const int cpr = K >> 3;
-  const int ctid = tid;                                   // consumers are threads 0 .. W*32-1
-  constexpr int MAXTOK = 5;
-  {
-    float amax[MAXTOK], sum[MAXTOK];
-#pragma unroll
-    for (int tok = 0; tok < MAXTOK; ++tok) { amax[tok] = 0.f; sum[tok] = 0.f; }
-    for (int c = ctid; c < cpr; c += W * 32) {
-#pragma unroll
-      for (int tok = 0; tok < MAXTOK; ++tok) {
-        if (tok < M) {
-          const uint4 v = *reinterpret_cast<const uint4*>(x + (int64_t)tok * K + 8 * c);
-          const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(h2[i]);
-            amax[tok] = fmaxf(amax[tok], fmaxf(fabsf(f.x), fabsf(f.y)));
-            sum[tok] += f.x + f.y;
-          }
-        }
-      }
-    }
-#pragma unroll
-    for (int tok = 0; tok < MAXTOK; ++tok) {
-      if (tok < M) {
-#pragma unroll
-        for (int o = 16; o; o >>= 1) {
-          amax[tok] = fmaxf(amax[tok], __shfl_xor_sync(0xffffffffu, amax[tok], o));
-          sum[tok] += __shfl_xor_sync(0xffffffffu, sum[tok], o);
-        }
-        if (lane == 0) { wred[(2 * tok) * W + warp] = amax[tok]; wred[(2 * tok + 1) * W + warp] = sum[tok]; }
-      }
-    }
-  }
-  consumer_sync<CW>();
-  float inv[MAXTOK];
-#pragma unroll
-  for (int tok = 0; tok < MAXTOK; ++tok) {
-    inv[tok] = 0.f;
-    if (tok < M) {
-      float amax = 0.f, sum = 0.f;
-#pragma unroll
-      for (int w = 0; w < W; ++w) { amax = fmaxf(amax, wred[(2 * tok) * W + w]); sum += wred[(2 * tok + 1) * W + w]; }
-      inv[tok] = amax > 0.f ? GV_QMAX / amax : 0.f;
-      if (ctid == 0) { tokf[2 * tok] = amax / GV_QMAX; tokf[2 * tok + 1] = sum; }
-    }
-  }
-  for (int c = ctid; c < cpr; c += W * 32) {
-#pragma unroll
-    for (int tok = 0; tok < MAXTOK; ++tok) {
-      if (tok < M) {
-        const uint4 v = *reinterpret_cast<const uint4*>(x + (int64_t)tok * K + 8 * c);   // second read hits L1/L2
-        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
-        int qv[8];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __half22float2(h2[i]);
-          qv[2 * i] = __float2int_rn(f.x * inv[tok]);
-          qv[2 * i + 1] = __float2int_rn(f.y * inv[tok]);
-        }
-        uint32_t lb[GV_LIMBS][2] = {};
-#pragma unroll
-        for (int sidx = 0; sidx < 8; ++sidx) {
-          constexpr int PI[8] = {0, 2, 1, 3, 4, 6, 5, 7};
-          int v0 = qv[PI[sidx]];
-          const int lo = (int)(int8_t)(v0 & 0xFF);
-          v0 = (v0 - lo) >> 8;
-          const int mid = (int)(int8_t)(v0 & 0xFF);
-          const int hi = (v0 - mid) >> 8;
-          lb[0][sidx >> 2] |= (uint32_t)(hi & 0xFF) << (8 * (sidx & 3));
-          lb[1][sidx >> 2] |= (uint32_t)(mid & 0xFF) << (8 * (sidx & 3));
-          lb[2][sidx >> 2] |= (uint32_t)(lo & 0xFF) << (8 * (sidx & 3));
-        }
-#pragma unroll
-        for (int l = 0; l < GV_LIMBS; ++l)
-          *reinterpret_cast<uint2*>(limbs + (size_t)(GV_LIMBS * tok + l) * lld + 8 * c) = make_uint2(lb[l][0], lb[l][1]);
-      }
-    }
-  }
-  consumer_sync<CW>();
+  gv_quantize_tokens<W>(x, M, K, limbs, lld, tokf, wred, tid, warp, lane);
 
   int slot = 0;                                           // ring position, advanced like the producer's
   uint32_t ph = 0, tcount = 0;
@@ -942,6 +952,157 @@ static int launch_gv_i8(const QuipLinearDesc* d, const __half* x, const __half* 
   return QUIP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// int8 path, streaming variant for very many row blocks (stacked / grouped matrices, >= 32 row blocks per SM):
+// every warp owns whole row blocks and streams their k run straight from global memory into a register ring
+// (8 x 512 B in flight per warp, 24 warps per SM), accumulates alone and writes its 16 x M outputs itself.  No
+// shared-memory ring, no producer, no barrier after the token prologue: the same shape as a plain read loop
+// (tools/read_bw.cu: 6.7-7.0 TB/s read-only on this GPU) with ~33 instructions of math per 512 bytes.
+// Measured on a 352256 x 4096 matrix, one token: 5.15 TB/s = 78 % of the HBM copy peak (2-bit), 6.7 TB/s
+// (4-bit); the cooperative bulk-copy kernel above stays at 3.8 TB/s there (its ring alone, math removed, moves
+// 4.4 TB/s) but is the faster one for a single layer, where nothing is steady and latency is everything
+// (4096 x 4096: 4.1 us against 8.7 us).
+// ---------------------------------------------------------------------------------------------
+constexpr int GS_WARPS = 8;            // per CTA; 3 CTAs per SM
+constexpr int GS_D = 8;                // super-blocks in flight per warp
+
+template <int BITS, int NT8>
+__global__ void __launch_bounds__(GS_WARPS * 32, 3)
+qgemv_i8_stream_kernel(const uint32_t* __restrict__ q, const __half* __restrict__ x, const float* __restrict__ scales,
+                       const float* __restrict__ zeros, const __half* __restrict__ bias, __half* __restrict__ z, int M,
+                       int K, int N) {
+  constexpr int W = GS_WARPS, D = BITS == 2 ? GS_D : GS_D / 2;
+  constexpr float HI_ROW_SCALE = BITS == 2 ? 0.25f : 0.0625f;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int KSB = K >> 7, NRB = N >> 4;
+  const int ncol = GV_LIMBS * M;
+  const int lld = K + 32;
+  const int warps_total = gridDim.x * W;
+  const int nsb_pad = (KSB + D - 1) / D * D;              // slot = sb % D, the same in every row block
+
+  int8_t* limbs = reinterpret_cast<int8_t*>(smem_raw);
+  float* tokf = reinterpret_cast<float*>(smem_raw + (((size_t)ncol * lld + 15) & ~(size_t)15));
+  float* wred = tokf + 16;
+
+  // ---- the ring: slot d holds super-block sb (sb % D == d) of the current or the next row block ----
+  GvRegs<BITS> ring[D];
+  const int rb0 = blockIdx.x * W + warp;
+  auto fetch = [&](int rb, int sb, GvRegs<BITS>& dst) {
+    if (rb < NRB && sb < KSB) gv_load<BITS>(q + ((int64_t)rb * KSB + sb) * sb_words(BITS), lane, dst);
+  };
+#pragma unroll
+  for (int d = 0; d < D; ++d) fetch(rb0, d, ring[d]);     // weights first: independent of the previous kernel
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  gv_quantize_tokens<W>(x, M, K, limbs, lld, tokf, wred, tid, warp, lane);
+
+  for (int rb = rb0; rb < NRB; rb += warps_total) {
+    const int n0 = rb * 16 + g;
+    const float sc0 = __ldg(scales + n0), sc1 = __ldg(scales + n0 + 8);
+    const float ze0 = __ldg(zeros + n0), ze1 = __ldg(zeros + n0 + 8);
+    const float bi0 = bias ? __half2float(__ldg(bias + n0)) : 0.f, bi1 = bias ? __half2float(__ldg(bias + n0 + 8)) : 0.f;
+    int acc[NT8][2][4];
+#pragma unroll
+    for (int b = 0; b < NT8; ++b)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[b][0][c] = acc[b][1][c] = 0;
+
+    for (int sb0 = 0; sb0 < nsb_pad; sb0 += D) {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const int sb = sb0 + d;
+        if (sb < KSB) {
+          const int8_t* lk = limbs + sb * 128 + 8 * t;
+          uint32_t xb[4][NT8][2];
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt) {
+              const uint2 v = *reinterpret_cast<const uint2*>(lk + (size_t)min(nt * 8 + g, ncol - 1) * lld + ch * 32);
+              xb[ch][nt][0] = v.x; xb[ch][nt][1] = v.y;
+            }
+          auto do_chunk = [&](auto chc) {
+            constexpr int CH = decltype(chc)::value;
+            uint32_t a[4];
+            gv_expand_i8<BITS, CH>(ring[d], a);
+#pragma unroll
+            for (int nt = 0; nt < NT8; ++nt) imma16832(acc[nt][CH & 1], a, xb[CH][nt]);
+          };
+          do_chunk(std::integral_constant<int, 0>{});
+          do_chunk(std::integral_constant<int, 1>{});
+          do_chunk(std::integral_constant<int, 2>{});
+          do_chunk(std::integral_constant<int, 3>{});
+        }
+        // refill the slot with the super-block D ahead, possibly in this warp's next row block
+        int frb = rb, fsb = sb + D;
+        if (fsb >= nsb_pad) { fsb -= nsb_pad; frb += warps_total; }
+        fetch(frb, fsb, ring[d]);
+      }
+    }
+
+    // ---- epilogue inside the warp: limb column c of a token sits in lane t = (c % 8) / 2, register c % 2 ----
+#pragma unroll
+    for (int tok = 0; tok < (NT8 == 1 ? 2 : 5); ++tok) {
+      if (tok < M) {
+        float dot0 = 0.f, dot1 = 0.f;                     // rows g and g+8
+#pragma unroll
+        for (int l = 0; l < GV_LIMBS; ++l) {
+          const int col = GV_LIMBS * tok + l, nt = col >> 3, cc = col & 7, st = cc >> 1, reg = cc & 1;
+          const int v0 = acc[nt][0][reg] + acc[nt][1][reg], v1 = acc[nt][0][2 + reg] + acc[nt][1][2 + reg];
+          const float f0 = (float)__shfl_sync(0xffffffffu, v0, 4 * g + st);
+          const float f1 = (float)__shfl_sync(0xffffffffu, v1, 4 * g + st);
+          const float wgt = l == 0 ? 65536.f : (l == 1 ? 256.f : 1.f);
+          dot0 += wgt * f0;
+          dot1 += wgt * f1;
+        }
+        if (t == 0) {
+          const float sm = tokf[2 * tok], S = tokf[2 * tok + 1];
+          z[(int64_t)tok * N + n0] = __float2half_rn(sc0 * (sm * dot0) - ze0 * S + bi0);
+          z[(int64_t)tok * N + n0 + 8] = __float2half_rn(sc1 * (sm * HI_ROW_SCALE * dot1) - ze1 * S + bi1);
+        }
+      }
+    }
+  }
+}
+
+template <int BITS, int NT8>
+static int launch_gv_i8_stream(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M,
+                               cudaStream_t s) {
+  const size_t limb_bytes = ((size_t)GV_LIMBS * M * (d->K + 32) + 15) & ~(size_t)15;
+  const size_t smem = limb_bytes + (size_t)(16 + 10 * GS_WARPS) * sizeof(float);
+  auto kern = qgemv_i8_stream_kernel<BITS, NT8>;
+  static size_t attr_smem[64] = {0};
+  static int occ[64] = {0};
+  int dev = 0;
+  QUIP_CUDA(cudaGetDevice(&dev));
+  dev &= 63;
+  if (smem > attr_smem[dev]) {
+    QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[dev] = smem;
+    occ[dev] = 0;
+  }
+  if (occ[dev] == 0) {
+    QUIP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[dev], kern, GS_WARPS * 32, smem));
+    if (occ[dev] < 1) occ[dev] = 1;
+  }
+  int grid = occ[dev] * num_sms();
+  const int need = ceil_div(d->N / 16, GS_WARPS);
+  if (grid > need) grid = need;
+  const uint32_t* qw = reinterpret_cast<const uint32_t*>(d->qweight);
+  const float *sc = d->scales, *ze = d->zeros;
+  int K = d->K, N = d->N;
+  void* args[] = {(void*)&qw, (void*)&x, (void*)&sc, (void*)&ze, (void*)&bias, (void*)&z, (void*)&M, (void*)&K, (void*)&N};
+  if (int e = launch_pdl((const void*)kern, dim3(grid), dim3(GS_WARPS * 32), smem, s, args)) return e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QUIP_OK;
+}
+
+static bool gv_stream_fits(int K, int M) {
+  return (size_t)GV_LIMBS * M * (K + 32) + 1024 <= (size_t)48 * 1024;      // four CTAs per SM
+}
+
 template <int BITS, int NT8, int RBC, int CW>
 static int launch_gv_i8_tma(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M,
                             cudaStream_t s) {
@@ -996,6 +1157,13 @@ int qgemv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* 
   if (rbc != 1 && rbc != 2) rbc = (d->N / 16 >= 4 * num_sms()) ? 2 : 1;
   if (g_gv_int && d->bits != 3 && M <= 5) {
     const int nt8 = M <= 2 ? 1 : 2;
+    if (g_gv_tma && g_gv_stream && d->N / 16 >= g_gv_stream * num_sms() && gv_stream_fits(d->K, M)) {
+      // many row blocks per warp slot (stacked / grouped matrices): every warp streams whole row blocks
+      if (d->bits == 2 && nt8 == 1) return launch_gv_i8_stream<2, 1>(d, x, bias, z, M, s);
+      if (d->bits == 2 && nt8 == 2) return launch_gv_i8_stream<2, 2>(d, x, bias, z, M, s);
+      if (d->bits == 4 && nt8 == 1) return launch_gv_i8_stream<4, 1>(d, x, bias, z, M, s);
+      if (d->bits == 4 && nt8 == 2) return launch_gv_i8_stream<4, 2>(d, x, bias, z, M, s);
+    }
     if (g_gv_tma) {
       int trbc = g_gv_rbc;
       if (trbc != 1 && trbc != 2) trbc = 2;

@@ -125,7 +125,8 @@ def test_qgemm_skinny_vs_oracle(bits, M, symmetric):
 @pytest.mark.parametrize('bits', [2, 3, 4])
 @pytest.mark.parametrize('M', [1, 2, 4, 5, 6, 8])
 @pytest.mark.parametrize('cfg', [dict(gv_int=1, gv_rbc=0), dict(gv_int=1, gv_rbc=2), dict(gv_int=0, gv_rbc=1),
-                                 dict(gv_int=1, gv_tma=0, gv_rbc=1, gv_persist=0), dict(gv_int=1, gv_tma=0, gv_rbc=2)])
+                                 dict(gv_int=1, gv_tma=0, gv_rbc=1, gv_persist=0), dict(gv_int=1, gv_tma=0, gv_rbc=2),
+                                 dict(gv_int=1, gv_stream=1)])
 def test_qgemv_whole_k_kernels(bits, M, cfg):
     """The few-token kernels (int8 tensor path for <= 5 tokens, offset-free fp16 path above): odd numbers of k
     super-blocks, ragged row tiles, a token with a huge outlier (the int8 path scales per token by amax) and an
@@ -136,7 +137,8 @@ def test_qgemv_whole_k_kernels(bits, M, cfg):
     try:
         for k, v in cfg.items():
             lib.quip_config(k.encode(), v)
-        for (N, K) in [(176, 11008), (272, 1024), (4096, 4096)]:
+        shapes = [(2400, 11008), (4096, 4096)] if cfg.get('gv_stream') else [(176, 11008), (272, 1024), (4096, 4096)]
+        for (N, K) in shapes:
             codes, scales, zeros, X, bias, want = _qgemm_case(bits, N, K, M, False, bits * 10 + M)
             X = X.copy()
             X[0, 7] = f16(3000.0)                      # outlier: amax/sigma ~ 1000
@@ -150,7 +152,7 @@ def test_qgemv_whole_k_kernels(bits, M, cfg):
             if M > 1:
                 np.testing.assert_allclose(z[M - 1].astype(f32), bias.astype(f32), atol=2e-3)
     finally:
-        for k, v in dict(gv_int=1, gv_rbc=0, gv_persist=1, gv_tma=1).items():
+        for k, v in dict(gv_int=1, gv_rbc=0, gv_persist=1, gv_tma=1, gv_stream=32).items():
             lib.quip_config(k.encode(), v)
 
 

@@ -165,8 +165,8 @@ def main():
         res.append(bench_qgemm(32 * 11008, 4096, 16, 2, 1, 2, peaks)); print(res[-1], flush=True)
     if 'gemv' in what:
         lib = _lib.load()
-        keys = ('gemv', 'gv_int', 'gv_rbc', 'gv_persist', 'gv_tma', 'gv_cw')
-        defaults = dict(gemv=1, gv_int=1, gv_rbc=0, gv_persist=1, gv_tma=1, gv_cw=16)
+        keys = ('gemv', 'gv_int', 'gv_rbc', 'gv_persist', 'gv_tma', 'gv_cw', 'gv_stream')
+        defaults = dict(gemv=1, gv_int=1, gv_rbc=0, gv_persist=1, gv_tma=1, gv_cw=16, gv_stream=32)
 
         def run(N, K, M, bits, copies, **cfg):
             for k in keys:
@@ -174,6 +174,27 @@ def main():
             r = bench_qgemm(N, K, M, bits, 1, copies, peaks); r.update(cfg); res.append(r)
             print({k: (round(v, 3) if isinstance(v, float) else v) for k, v in r.items()
                    if k not in ('TFLOPs', 'tensor_frac', 'kind', 'path')}, flush=True)
+        if 'route' in what:
+            for (N, K) in [(4096, 4096), (11008, 4096), (4096, 11008), (12288, 4096), (22016, 4096)]:
+                copies = max(2, int(300e6 // (N * K // 4)))
+                for M in (1, 2):
+                    run(N, K, M, 2, copies, gv_tma=1, gv_stream=0)
+                    run(N, K, M, 2, copies, gv_tma=0, gv_stream=0, gv_rbc=1)
+                    run(N, K, M, 2, copies, gv_tma=0, gv_stream=0, gv_rbc=2)
+                    run(N, K, M, 2, copies, gv_stream=1)
+        if 'probe' in what:
+            for bits in (2, 4):
+                for st in (0, 8):
+                    for M in (1, 2, 4):
+                        run(32 * 11008, 4096, M, bits, 2, gv_stream=st)
+            run(32 * 4096, 11008, 1, 2, 2, gv_stream=32)
+        if 'gemv3' in what:
+            for (N, K) in [(32 * 11008, 4096), (32 * 4096, 11008), (3 * 4096, 4096), (2 * 11008, 4096)]:
+                copies = max(2, int(300e6 // (N * K // 4)))
+                for M in (1, 2, 4):
+                    for st in (0, 1, 8):
+                        run(N, K, M, 2, copies, gv_stream=st)
+            run(32 * 11008, 4096, 1, 4, 2, gv_stream=32)
         if 'gemv2' in what:
             for (N, K) in shapes + [(32 * 11008, 4096)]:
                 copies = max(2, int(300e6 // (N * K // 4)))
@@ -181,7 +202,7 @@ def main():
                     for cw in (8, 16):
                         for rbc in (1, 2):
                             run(N, K, M, 2, copies, gv_cw=cw, gv_rbc=rbc)
-        for (N, K) in ([] if 'gemv2' in what else shapes + [(32 * 11008, 4096)]):
+        for (N, K) in ([] if ('gemv2' in what or 'gemv3' in what or 'probe' in what or 'route' in what) else shapes + [(32 * 11008, 4096)]):
             copies = max(2, int(300e6 // (N * K // 4)))
             for M in (1, 2, 4, 8):
                 for rbc in (1, 2):
@@ -190,7 +211,7 @@ def main():
                         run(N, K, M, 2, copies, gv_tma=0, gv_rbc=rbc)
                     run(N, K, M, 2, copies, gv_int=0, gv_rbc=rbc)
         for bits in (3, 4):
-            for g in ((1,) if 'gemv2' in what else (0, 1)):
+            for g in (() if ('gemv3' in what or 'probe' in what or 'route' in what) else (1,) if 'gemv2' in what else (0, 1)):
                 run(11008, 4096, 1, bits, 8, gemv=g)
         for k in keys:
             lib.quip_config(k.encode(), defaults[k])
