@@ -361,6 +361,16 @@ def main():
             for g in groups:
                 g.dissolve()
             out['decode'] = decode_leg(model, dev, pk)
+            # the reference's benchmark() (opt.py:431-482): token-by-token through the whole HF model with a KV cache
+            sec, _ = evalloop.decode_benchmark(model, ids_dev[0][:, :48])
+            out['decode']['hf_decode'] = dict(tokens_per_s=1.0 / sec, median_ms_per_token=sec * 1e3, tokens=48,
+                                              note='quip_b200.evalloop.decode_benchmark: eager HF forward per token '
+                                                   '(host launch overhead included), batch 1')
+            from quip_b200.decode import graph_decode_benchmark
+            gsec, _ = graph_decode_benchmark(model, ids_dev[0][:, :48], max_len=64)
+            out['decode']['graph_decode'] = dict(tokens_per_s=1.0 / gsec, median_ms_per_token=gsec * 1e3, tokens=48,
+                                                 note='quip_b200.decode.GraphDecoder: the same decode step (attention, norms, '
+                                                      'static KV cache of 64, lm_head) replayed from one CUDA graph, batch 1')
         except Exception as e:                      # the decode leg is an extra; never lose the headline over it
             out['decode'] = dict(error=repr(e)[:200])
     if world == 1 and not a.no_cpu_baseline:

@@ -1,0 +1,146 @@
+"""Token-by-token decode of a packed Llama model from one CUDA graph.
+
+The reference's `benchmark()` (opt.py:431-482, llama.py via the same code) times an eager HF forward per
+token with a growing KV cache; with the few-token kernels of this package one token's GPU work is a few
+milliseconds while the eager Python path around it costs more than that in launch overhead.  `GraphDecoder`
+is the same computation with everything a CUDA graph needs made static:
+
+  * a KV cache of fixed length `max_len` per layer, written at the current position with `index_copy_`;
+  * the position as a device tensor (advanced inside the graph), rotary cos/sin gathered from a table;
+  * attention over the whole cache under a mask `arange(max_len) <= position`.
+
+The decoder layers' own modules are reused (input_layernorm, the seven QuantLinear / nn.Linear projections,
+post_attention_layernorm, final norm, lm_head): same weights, same kernels as `model(...)`; only the glue
+between them is restated.  Llama family only (MHA or GQA); OPT keeps the eager path.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+def _rotate_half(x):
+    h = x.shape[-1] // 2
+    return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+
+class GraphDecoder:
+    def __init__(self, model, max_len=256, batch=1):
+        cfg = model.config
+        assert cfg.model_type == 'llama', 'GraphDecoder covers the Llama family'
+        self.model, self.max_len, self.batch = model, int(max_len), int(batch)
+        self.dev = next(iter(model.parameters())).device
+        self.layers = list(model.model.layers)
+        self.nh = cfg.num_attention_heads
+        self.nkv = getattr(cfg, 'num_key_value_heads', None) or self.nh
+        self.hd = getattr(cfg, 'head_dim', None) or cfg.hidden_size // self.nh
+        dt = torch.float16
+        # rotary table with the model's own module (HF default rope: positions 0 .. max_len-1)
+        pos = torch.arange(self.max_len, device=self.dev)[None, :]
+        with torch.no_grad():
+            cos, sin = model.model.rotary_emb(torch.zeros(1, 1, cfg.hidden_size, device=self.dev, dtype=dt), pos)
+        self.cos, self.sin = cos[0].to(dt).contiguous(), sin[0].to(dt).contiguous()        # (max_len, head_dim)
+        L, B = len(self.layers), self.batch
+        self.k_cache = torch.zeros(L, B, self.nkv, self.max_len, self.hd, dtype=dt, device=self.dev)
+        self.v_cache = torch.zeros_like(self.k_cache)
+        self.position = torch.zeros(1, dtype=torch.long, device=self.dev)
+        self.tokens = torch.zeros(B, dtype=torch.long, device=self.dev)
+        self.logits = None
+        self.graph = None
+        self._arange = torch.arange(self.max_len, device=self.dev)
+        self._pos_host = 0
+
+    def reset(self):
+        self._pos_host = 0
+        self.position.zero_()
+        self.k_cache.zero_()
+        self.v_cache.zero_()
+
+    # one decode step on the static buffers (what the graph records)
+    def _step(self):
+        m = self.model.model
+        B, nh, nkv, hd = self.batch, self.nh, self.nkv, self.hd
+        pos = self.position
+        h = m.embed_tokens(self.tokens)[:, None, :]                                        # (B, 1, hidden)
+        cos = self.cos.index_select(0, pos)[None, None]                                    # (1, 1, 1, hd)
+        sin = self.sin.index_select(0, pos)[None, None]
+        mask = (self._arange <= pos)[None, None, None, :]                                  # (1, 1, 1, max_len)
+        for li, layer in enumerate(self.layers):
+            a = layer.self_attn
+            x = layer.input_layernorm(h)
+            q = a.q_proj(x).view(B, 1, nh, hd).transpose(1, 2)                             # (B, nh, 1, hd)
+            k = a.k_proj(x).view(B, 1, nkv, hd).transpose(1, 2)
+            v = a.v_proj(x).view(B, 1, nkv, hd).transpose(1, 2)
+            q = q * cos + _rotate_half(q) * sin
+            k = k * cos + _rotate_half(k) * sin
+            self.k_cache[li].index_copy_(2, pos, k)
+            self.v_cache[li].index_copy_(2, pos, v)
+            kk, vv = self.k_cache[li], self.v_cache[li]
+            if nkv != nh:
+                kk = kk.repeat_interleave(nh // nkv, dim=1)
+                vv = vv.repeat_interleave(nh // nkv, dim=1)
+            o = F.scaled_dot_product_attention(q, kk, vv, attn_mask=mask, scale=1.0 / math.sqrt(hd))
+            o = o.transpose(1, 2).reshape(B, 1, nh * hd)
+            h = h + a.o_proj(o)
+            x = layer.post_attention_layernorm(h)
+            mlp = layer.mlp
+            h = h + mlp.down_proj(F.silu(mlp.gate_proj(x)) * mlp.up_proj(x))
+        h = m.norm(h)
+        self.logits = self.model.lm_head(h)[:, 0, :]
+        self.position.add_(1)
+
+    def capture(self):
+        """Record one step.  The cache and position are restored afterwards, so capture is side-effect free."""
+        from .quant import QuantLinear
+        for mod in self.model.modules():                   # sibling groups launch on side streams: not while capturing
+            if isinstance(mod, QuantLinear) and getattr(mod, '_group', None) is not None:
+                raise RuntimeError('dissolve the sibling groups (quant.SiblingGroup.dissolve) before capturing')
+        pos0, k0, v0 = self.position.clone(), self.k_cache.clone(), self.v_cache.clone()
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(2):                             # lazy set-up (descriptors, workspaces) outside the graph
+                self._step()
+            self.position.copy_(pos0)
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self._step()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        self.position.copy_(pos0)
+        self.k_cache.copy_(k0)
+        self.v_cache.copy_(v0)
+        return self
+
+    def step(self, tokens):
+        """tokens (B,) -> logits (B, vocab) for the next position; advances the cache."""
+        if self._pos_host >= self.max_len:
+            raise ValueError(f'KV cache of {self.max_len} positions is full')
+        self._pos_host += 1
+        self.tokens.copy_(tokens.reshape(-1))
+        if self.graph is None:
+            with torch.no_grad():
+                self._step()
+        else:
+            self.graph.replay()
+        return self.logits
+
+
+def graph_decode_benchmark(model, input_ids, max_len=None, check=False):
+    """`decode_benchmark` (reference benchmark(), opt.py:431-482) through the graph: median seconds per token and,
+    with check, the perplexity of the fed sequence."""
+    import time
+
+    import numpy as np
+    ids = input_ids.reshape(-1).to(next(iter(model.parameters())).device)
+    dec = GraphDecoder(model, max_len=max_len or int(ids.numel()), batch=1).capture()
+    times, tot = [], 0.0
+    for i in range(ids.numel()):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        logits = dec.step(ids[i:i + 1])
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        if check and i != ids.numel() - 1:
+            tot += float(F.cross_entropy(logits.float(), ids[i + 1:i + 2]))
+    ppl = float(np.exp(tot / (ids.numel() - 1))) if check else None
+    return float(np.median(times)), ppl

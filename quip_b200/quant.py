@@ -246,9 +246,11 @@ def convert_ref_qweight(ref_qweight: torch.Tensor, K: int, N: int, bits: int) ->
 _workspaces = {}
 
 
-def _workspace(device, nbytes):
+def _workspace(device, nbytes, stream_ptr=None):
     """One workspace per (device, stream): kernels of different streams may run concurrently."""
-    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    if stream_ptr is None:
+        stream_ptr = torch.cuda.current_stream(device).cuda_stream
+    key = (device, stream_ptr)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -485,6 +487,8 @@ class QuantLinear(nn.Module):
             d.inv_scale = self.inv_scale.data_ptr() if use_scale else None
             d.V, d.U = self._side('v', self.infeatures), self._side('u', self.outfeatures)
             self._desc = d
+            self._desc_ref = C.byref(d)
+            self._ws_need = {}
         return self._desc
 
     # -- forward -------------------------------------------------------------------------------
@@ -508,12 +512,20 @@ class QuantLinear(nn.Module):
         if M:
             lib = _lib.load()
             d = self._descriptor()
-            need = C.c_size_t()
-            _lib.check(lib.quip_qlinear_workspace_bytes(C.byref(d), M, C.byref(need)))
-            ws = _workspace(x.device, need.value)
-            with torch.cuda.device(x.device):
-                _lib.check(lib.quip_qlinear_forward(C.byref(d), _lib.ptr(xh), _lib.ptr(y), M, _lib.ptr(ws), ws.numel(),
-                                                    C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+            need = self._ws_need.get(M)                 # per token count: one C call the first time, a dict hit after
+            if need is None:
+                nb = C.c_size_t()
+                _lib.check(lib.quip_qlinear_workspace_bytes(C.byref(d), M, C.byref(nb)))
+                need = self._ws_need[M] = nb.value
+            stream = torch.cuda.current_stream(x.device)
+            ws = _workspace(x.device, need, stream.cuda_stream)
+            if x.device.index == torch.cuda.current_device():
+                _lib.check(lib.quip_qlinear_forward(self._desc_ref, xh.data_ptr(), y.data_ptr(), M, ws.data_ptr(), ws.numel(),
+                                                    stream.cuda_stream))
+            else:
+                with torch.cuda.device(x.device):
+                    _lib.check(lib.quip_qlinear_forward(self._desc_ref, xh.data_ptr(), y.data_ptr(), M, ws.data_ptr(),
+                                                        ws.numel(), stream.cuda_stream))
         y = y.reshape(*x.shape[:-1], self.outfeatures)
         return y if dtype == torch.float16 else y.to(dtype)
 

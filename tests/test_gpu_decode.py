@@ -1,0 +1,49 @@
+"""Graph-captured Llama decode (quip_b200/decode.py) against the eager HF forward with a KV cache -- the loop the
+reference's benchmark() times (opt.py:431-482)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _tiny_llama(kv_heads):
+    from transformers import LlamaConfig
+    from quip_b200.synth import build_synthetic_model
+    cfg = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=kv_heads, vocab_size=320, max_position_embeddings=128)
+    return build_synthetic_model(cfg, torch.device('cuda:0'), bits=2, incoh='blocked', rescale=True, seed=5, seqlen=64)
+
+
+@pytest.mark.parametrize('kv_heads', [4, 2])
+def test_graph_decoder_matches_eager_hf_decode(kv_heads):
+    from quip_b200.decode import GraphDecoder
+    model = _tiny_llama(kv_heads)
+    ids = torch.randint(0, 320, (1, 14), generator=torch.Generator().manual_seed(3)).cuda()
+    with torch.no_grad():
+        past, want = None, []
+        for i in range(ids.shape[1]):
+            out = model(ids[:, i:i + 1], past_key_values=past, use_cache=True)
+            past = out.past_key_values
+            want.append(out.logits[0, -1].float())
+        dec = GraphDecoder(model, max_len=32)
+        eager = [dec.step(ids[0, i:i + 1])[0].float().clone() for i in range(ids.shape[1])]
+        dec.reset()
+        dec.capture()
+        graph = [dec.step(ids[0, i:i + 1])[0].float().clone() for i in range(ids.shape[1])]
+    for i, (w, e, g) in enumerate(zip(want, eager, graph)):
+        assert torch.equal(e, g), i                                   # replay == the recorded computation
+        err = float((g - w).norm() / w.norm())
+        assert err < 2e-2, (i, err)                                   # fp16 glue restated: same numbers up to rounding
+    with pytest.raises(ValueError):
+        for _ in range(40):
+            dec.step(ids[0, :1])
+
+
+def test_graph_decode_benchmark_reports_time_and_ppl():
+    from quip_b200.decode import graph_decode_benchmark
+    from quip_b200.evalloop import decode_benchmark
+    model = _tiny_llama(4)
+    ids = torch.randint(0, 320, (1, 12), generator=torch.Generator().manual_seed(4))
+    sec, ppl = graph_decode_benchmark(model, ids, check=True)
+    sec0, ppl0 = decode_benchmark(model, ids, check=True)
+    assert sec > 0 and abs(ppl - ppl0) / ppl0 < 2e-2
