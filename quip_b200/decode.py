@@ -49,6 +49,22 @@ class GraphDecoder:
         self.graph = None
         self._arange = torch.arange(self.max_len, device=self.dev)
         self._pos_host = 0
+        # q/k/v and gate/up read the same input: their chains of few-token kernels run on parallel branches
+        self._side = [torch.cuda.Stream(device=self.dev) for _ in range(2)]
+
+    def _parallel(self, x, mods):
+        """[m(x) for m in mods] with every module after the first on its own stream (graph branches when capturing)."""
+        main = torch.cuda.current_stream(self.dev)
+        outs = [None] * len(mods)
+        for i, m in enumerate(mods[1:], 1):
+            st = self._side[i - 1]
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                outs[i] = m(x)
+        outs[0] = mods[0](x)
+        for i in range(1, len(mods)):
+            main.wait_stream(self._side[i - 1])
+        return outs
 
     def reset(self):
         self._pos_host = 0
@@ -68,9 +84,10 @@ class GraphDecoder:
         for li, layer in enumerate(self.layers):
             a = layer.self_attn
             x = layer.input_layernorm(h)
-            q = a.q_proj(x).view(B, 1, nh, hd).transpose(1, 2)                             # (B, nh, 1, hd)
-            k = a.k_proj(x).view(B, 1, nkv, hd).transpose(1, 2)
-            v = a.v_proj(x).view(B, 1, nkv, hd).transpose(1, 2)
+            q, k, v = self._parallel(x, [a.q_proj, a.k_proj, a.v_proj])
+            q = q.view(B, 1, nh, hd).transpose(1, 2)                                       # (B, nh, 1, hd)
+            k = k.view(B, 1, nkv, hd).transpose(1, 2)
+            v = v.view(B, 1, nkv, hd).transpose(1, 2)
             q = q * cos + _rotate_half(q) * sin
             k = k * cos + _rotate_half(k) * sin
             self.k_cache[li].index_copy_(2, pos, k)
@@ -84,7 +101,8 @@ class GraphDecoder:
             h = h + a.o_proj(o)
             x = layer.post_attention_layernorm(h)
             mlp = layer.mlp
-            h = h + mlp.down_proj(F.silu(mlp.gate_proj(x)) * mlp.up_proj(x))
+            gate, up = self._parallel(x, [mlp.gate_proj, mlp.up_proj])
+            h = h + mlp.down_proj(F.silu(gate) * up)
         h = m.norm(h)
         self.logits = self.model.lm_head(h)[:, 0, :]
         self.position.add_(1)
