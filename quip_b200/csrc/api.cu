@@ -26,10 +26,10 @@ void set_error(const char* fmt, ...) {
 // implemented in qgemm_skinny.cu / qgemm_tc.cu
 int qgemm_skinny(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M, int ksplit,
                  float* part, int* counters, cudaStream_t s);
-int skinny_pick_ksplit(int N, int K, int rows_per_cta);
+int skinny_pick_ksplit(int N, int K, int rows_per_cta, int M);
 size_t skinny_workspace_bytes(int N, int M, int ksplit);
 int qgemv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M, cudaStream_t s);
-bool qgemv_fits(int K, int M);
+bool qgemv_fits(int K, int M, int bits);
 int qgemm_tc(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
              cudaStream_t s);
 int qgemm_tc2(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
@@ -99,7 +99,7 @@ static WsPlan plan_ws(const QuipLinearDesc* d, int64_t M) {
   p.zbuf = off; if (u_on) off += xn;
   p.bufC = off; if (u_on) off += xn;
   p.part = off;
-  if (M <= SKINNY_MAX_M) off += align_up(skinny_workspace_bytes(d->N, (int)M, skinny_pick_ksplit(d->N, d->K, 64)), 256);
+  if (M <= SKINNY_MAX_M) off += align_up(skinny_workspace_bytes(d->N, (int)M, skinny_pick_ksplit(d->N, d->K, 64, (int)M)), 256);
   p.total = off;
   return p;
 }
@@ -159,11 +159,11 @@ static int run_qgemm_untimed(const QuipLinearDesc* d, const __half* x2, const fl
     // the skinny kernel takes <= 32 tokens per launch and sums x itself
     for (int64_t m0 = 0; m0 < M; m0 += SKINNY_MAX_M) {
       int mc = (int)((M - m0) < SKINNY_MAX_M ? (M - m0) : SKINNY_MAX_M);
-      if (g_use_gemv && qgemv_fits(d->K, mc)) {
+      if (g_use_gemv && qgemv_fits(d->K, mc, d->bits)) {
         if (int e = qgemv(d, x2 + m0 * d->K, bias, z + m0 * d->N, mc, s)) return e;
         continue;
       }
-      int ksplit = M <= SKINNY_MAX_M ? skinny_pick_ksplit(d->N, d->K, 64) : 1;
+      int ksplit = skinny_pick_ksplit(d->N, d->K, 64, mc);
       if (int e = qgemm_skinny(d, x2 + m0 * d->K, bias, z + m0 * d->N, mc, ksplit,
                                reinterpret_cast<float*>(ws + p.part), reinterpret_cast<int*>(ws), s))
         return e;

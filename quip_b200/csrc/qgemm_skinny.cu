@@ -250,12 +250,18 @@ static int launch_skinny(const QuipLinearDesc* d, const __half* x, const __half*
   return QUIP_OK;
 }
 
-// Heuristic split: enough CTAs for >= 2 per SM, K slices of at least 512.
-int skinny_pick_ksplit(int N, int K, int rows_per_cta) {
+// Heuristic split: enough CTAs for >= 2 per SM, K slices of at least 512 -- and small enough that the staged
+// activations of M tokens fit shared memory (K = 28672 with 32 tokens needs 16 slices).
+int skinny_pick_ksplit(int N, int K, int rows_per_cta, int M) {
   int tiles = ceil_div(N, rows_per_cta);
   int ksb = K / 128;
   int ks = 1;
   while (tiles * ks < 296 && ksb / (ks * 2) >= 4) ks *= 2;
+  const int tok = M <= 8 ? 8 : (M <= 16 ? 16 : 32);
+  auto smem = [&](int k) {
+    return (size_t)tok * (ceil_div(ksb, k) * 128 + SK_XPAD) * sizeof(__half) + (size_t)(SK_WARPS * tok * 72 + tok) * sizeof(float);
+  };
+  while (smem(ks) > 200 * 1024 && ks < ksb) ks *= 2;
   return ks;
 }
 

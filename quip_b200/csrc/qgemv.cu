@@ -1142,17 +1142,30 @@ static bool gv_tma_fits(int K, int M, int bits, int nt8, int rbc, int cw) {
   return fixed + (size_t)(2 * rbc + 2) * (stage + 16) <= (size_t)227 * 1024 - 256;
 }
 
-// shared memory the whole-K kernels need for M tokens; the caller falls back to the split-K kernel above this
-bool qgemv_fits(int K, int M) {
-  if (M > 8 || K < 128 * GV_WARPS) return false;
+// shared memory of the register-ring int8 kernel (three token bytes per k + reduction buffers)
+static bool gv_i8_ldg_fits(int K, int M, int nt8) {
+  const size_t smem = (size_t)GV_LIMBS * M * (K + 32) + (size_t)(2 * GV_WARPS * 8 * nt8 * 36) * sizeof(int) + 1024;
+  return smem <= (size_t)227 * 1024 - 256;
+}
+// ... and of the fp16 kernel (one fp16 per k per token)
+static bool gv_f16_fits(int K, int M) {
   const size_t smem = (size_t)M * (K + GV_XPAD) * sizeof(__half) +
                       (size_t)(2 * GV_WARPS * 8 * 36 + GV_WARPS * 16) * sizeof(float) + 16;
   return smem <= 200 * 1024;
 }
 
+// Can a whole-K kernel take M tokens of this K?  (Llama-2-70B's down_proj, K = 28672, fits three tokens; above
+// that the caller uses the split-K kernel.)
+bool qgemv_fits(int K, int M, int bits) {
+  if (M > 8 || K < 128 * GV_WARPS) return false;
+  if (g_gv_int && bits != 3 && M <= 5 && (gv_i8_ldg_fits(K, M, M <= 2 ? 1 : 2) || gv_tma_fits(K, M, bits, M <= 2 ? 1 : 2, 1, 8)))
+    return true;
+  return gv_f16_fits(K, M);
+}
+
 int qgemv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* z, int M, cudaStream_t s) {
   QUIP_CHECK_ARG(M >= 1 && M <= 8, "qgemv handles 1..8 tokens (got %d)", M);
-  QUIP_CHECK_ARG(qgemv_fits(d->K, M), "qgemv: K=%d with %d tokens does not fit shared memory", d->K, M);
+  QUIP_CHECK_ARG(qgemv_fits(d->K, M, d->bits), "qgemv: K=%d with %d tokens does not fit shared memory", d->K, M);
   int rbc = g_gv_rbc;
   if (rbc != 1 && rbc != 2) rbc = (d->N / 16 >= 4 * num_sms()) ? 2 : 1;
   if (g_gv_int && d->bits != 3 && M <= 5) {
@@ -1185,7 +1198,7 @@ int qgemv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* 
       }
     }
 #define QUIP_GVI(B, T, DD)                                                                  \
-  if (d->bits == B && nt8 == T) {                                                           \
+  if (d->bits == B && nt8 == T && gv_i8_ldg_fits(d->K, M, T)) {                             \
     if (rbc == 2) return launch_gv_i8<B, T, 2, DD>(d, x, bias, z, M, s);                    \
     return launch_gv_i8<B, T, 1, 2 * DD>(d, x, bias, z, M, s);                              \
   }
@@ -1197,6 +1210,7 @@ int qgemv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* 
     if (rbc == 2) return launch_gv<B, 1, 2, DD>(d, x, bias, z, M, s);                       \
     return launch_gv<B, 1, 1, 2 * DD>(d, x, bias, z, M, s);                                 \
   }
+  QUIP_CHECK_ARG(gv_f16_fits(d->K, M), "qgemv: K=%d with %d tokens does not fit shared memory", d->K, M);
   QUIP_GV(2, 2) QUIP_GV(3, 2) QUIP_GV(4, 1)
 #undef QUIP_GV
   set_error("qgemv: unsupported bits=%d", d->bits);

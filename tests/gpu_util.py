@@ -69,3 +69,43 @@ def run_qgemm(codes, scales, zeros, bits, X, path, bias=None, symmetric=False):
     torch.cuda.synchronize()
     assert int(ws[:_lib.WS_HEADER_BYTES].max()) == 0, 'split-K counters must be left zeroed'
     return z.cpu().numpy(), xsum.cpu().numpy()
+
+
+def torch_reference_forward(ql, x):
+    """fp32 restatement of QuantLinear.forward in plain torch, from the module's own buffers and pass descriptors:
+    y = gather_u(passes_u(passes_v(gather_v(x * 1/s)) @ Q^T)) + bias, Q = scales * codes - zeros.  No fp16 rounding
+    between the stages: the CUDA path must agree within the fp16 error budget."""
+    d = ql._descriptor()
+    K, N = ql.infeatures, ql.outfeatures
+    dev = x.device
+
+    def side(sd, h, name):
+        n = sd.n
+        for i in range(sd.npass if n else 0):
+            ps = sd.passes[i]
+            F_ = getattr(ql, f'{name}_f{i}').float()
+            p, nblk = ps.p, ps.nblk
+            if F_.shape[0] == 1 and nblk > 1:
+                F_ = F_.expand(nblk, p, p)
+            if ps.strided:
+                h3 = h.reshape(-1, p, nblk)                                   # element j of block b at j*nblk + b
+                h = torch.einsum('bij,mjb->mib', F_, h3).reshape(-1, n)
+            else:
+                h3 = h.reshape(-1, nblk, p)
+                h = torch.einsum('bij,mbj->mbi', F_, h3).reshape(-1, n)
+        return h
+
+    h = x.float().reshape(-1, K)
+    if d.V.n or d.inv_scale:
+        idx = ql.v_idx.long() if (d.V.n and d.V.idx) else torch.arange(K, device=dev)
+        h = h[:, idx] * (ql.inv_scale.float()[idx] if d.inv_scale else 1.0)
+    h = side(d.V, h, 'v')
+    codes = Q.unpack_codes(ql.qweight, N, K, ql.bits).float()
+    Qm = ql.scales.float().reshape(-1, 1) * codes - ql.zeros.float().reshape(-1, 1)
+    z = h @ Qm.T
+    z = side(d.U, z, 'u')
+    if d.U.n and d.U.idx:
+        z = z[:, ql.u_idx.long()]
+    if ql.bias is not None:
+        z = z + ql.bias.float()
+    return z
