@@ -127,15 +127,19 @@ def test_fused_side_kernel_equals_the_separate_kernels(K, N, incoh, bias, M):
     assert float((y1 == y0).float().mean()) > 0.99
 
 
-@pytest.mark.parametrize('K,N', [(8192, 1024), (7168, 7168), (28672, 8192), (4096, 11008)])
-def test_other_model_shapes_against_torch_fp32(K, N):
+@pytest.mark.parametrize('K,N,bits,incoh', [(8192, 1024, 2, 'blocked'), (7168, 7168, 2, 'blocked'), (28672, 8192, 2, 'blocked'),
+                                             (4096, 11008, 2, 'blocked'), (4096, 4096, 3, 'blocked'), (11008, 4096, 4, 'blocked'),
+                                             (2048, 8192, 2, 'blocked'), (768, 3072, 4, None), (4096, 4096, 2, 'kron'),
+                                             (3072, 768, 3, 'noperm')])
+def test_other_model_shapes_against_torch_fp32(K, N, bits, incoh):
     """Layer shapes of the other configurations (Llama-2-70B: 8192 = 128 x 64, 28672 = 448 x 64; OPT-30b: 7168 =
     224 x 32) through every token-count route -- few-token kernels, split-K, tcgen05 -- against an fp32 torch
     restatement of the same pipeline built from the module's own buffers."""
     from gpu_util import torch_reference_forward
     from quip_b200 import quant as Q
     from quip_b200.synth import synth_layer_parts
-    tp = synth_layer_parts(K=K, N=N, bits=2, incoh='blocked', rescale=True, bias=(N == 1024), seed=K + N, qfn='a')
+    tp = synth_layer_parts(K=K, N=N, bits=bits, incoh=incoh, rescale=incoh is not None, bias=(N in (1024, 8192, 3072)),
+                           seed=K + N, qfn='a')
     ql = Q.QuantLinear(infeatures=K, outfeatures=N, **Q.spec_from_parts(tp)).cuda()
     ql.pack_parts(tp)
     x = (torch.randn(40, K, device='cuda') * (1 + 3 * torch.rand(K, device='cuda'))).half()
@@ -143,7 +147,7 @@ def test_other_model_shapes_against_torch_fp32(K, N):
     for M in (1, 5, 8, 20, 40):
         y = ql(x[:M]).float()
         err = float((y - want[:M]).norm() / want[:M].norm())
-        assert err < 1.5e-3, (K, N, M, err)
+        assert err < 1.5e-3, (K, N, bits, incoh, M, err)
 
 
 def test_sibling_group_overlap_is_bit_identical():
