@@ -154,3 +154,33 @@ def test_make_quant_swaps_exactly_the_named_layers():
     assert net.layers[0].keep.bits == 3
     with pytest.raises(NotImplementedError):
         Q.QuantLinear(8, 128, 128)
+
+
+def test_fragment_order_matches_the_header_formula():
+    """QuipPass.factors_frag (include/quip_b200.h): word (((blk*(p/8) + nt)*(p/32) + j)*32 + lane)*4 + q holds
+    F[blk][8nt + lane/4][k0], [k0+1] with k0 = 32j + 16(q/2) + 8(q%2) + 2(lane%4)."""
+    import numpy as np
+    import torch
+    from quip_b200.quant import fragment_order
+    for nblk, p in [(3, 64), (2, 32)]:
+        f = torch.arange(nblk * p * p, dtype=torch.float32).reshape(nblk, p, p).half()
+        frag = fragment_order(f).reshape(-1, 2).numpy()              # words of two halves
+        F_ = f.numpy()
+        rng = np.random.default_rng(p)
+        for _ in range(200):
+            blk, nt, j = rng.integers(nblk), rng.integers(p // 8), rng.integers(p // 32)
+            lane, q = rng.integers(32), rng.integers(4)
+            word = (((blk * (p // 8) + nt) * (p // 32) + j) * 32 + lane) * 4 + q
+            k0 = 32 * j + 16 * (q // 2) + 8 * (q % 2) + 2 * (lane % 4)
+            row = 8 * nt + lane // 4
+            assert frag[word, 0] == F_[blk, row, k0] and frag[word, 1] == F_[blk, row, k0 + 1]
+
+
+def test_abi_v2_structs_carry_the_optional_pointers():
+    from quip_b200 import _lib
+    assert 'factors_frag' in [n for n, _ in _lib.QuipPass._fields_]
+    assert 'inv_idx' in [n for n, _ in _lib.QuipSide._fields_]
+    s = _lib.QuipSide()
+    assert not s.inv_idx and not s.passes[0].factors_frag          # NULL by default: the C side takes the unfused routes
+    hdr = open(os.path.join(ROOT, 'include', 'quip_b200.h')).read()
+    assert 'QUIP_ABI_VERSION 2' in hdr and 'factors_frag' in hdr and 'inv_idx' in hdr
