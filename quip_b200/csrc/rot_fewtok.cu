@@ -48,16 +48,27 @@ pass_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
   const int s0 = part * steps_per_part, s1 = min(ksteps, s0 + steps_per_part);
 
   // ---- factor rows g and g+8 of this tile: everything requested up front (weights: no dependency) ----
-  const __half* frow = F + ((int64_t)(shared ? 0 : b) * p + rt * 16 + g) * p + 4 * t;
-  uint2 a_lo[FT_STEPS], a_hi[FT_STEPS];
+  // Pairs of k16 steps are one 128-bit load per row: within a 32-wide k block a lane owns 8 consecutive k
+  // (32u + 8t ..), the first four feeding the MMA of step 2u, the last four that of step 2u+1 (the token operand is
+  // read with the same labelling).  A trailing odd step (p = 688 = 21 x 32 + 16) uses 64-bit loads of 4 consecutive k.
+  const __half* frow = F + ((int64_t)(shared ? 0 : b) * p + rt * 16 + g) * p;
+  constexpr int FT_PAIRS = FT_STEPS / 2;
+  uint4 a_lo[FT_PAIRS], a_hi[FT_PAIRS];
+  const int npair = live ? (s1 - s0) / 2 : 0;             // s0 is even (steps_per_part is)
+  const bool tail = live && ((s1 - s0) & 1);
 #pragma unroll
-  for (int s = 0; s < FT_STEPS; ++s) {
-    a_lo[s] = make_uint2(0u, 0u);
-    a_hi[s] = make_uint2(0u, 0u);
-    if (live && s0 + s < s1) {
-      a_lo[s] = ldg_nc_v2(frow + (s0 + s) * 16);
-      a_hi[s] = ldg_nc_v2(frow + (int64_t)8 * p + (s0 + s) * 16);
+  for (int u = 0; u < FT_PAIRS; ++u) {
+    a_lo[u] = make_uint4(0u, 0u, 0u, 0u);
+    a_hi[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (u < npair) {
+      a_lo[u] = ldg_nc_v4(frow + (s0 + 2 * u) * 16 + 8 * t);
+      a_hi[u] = ldg_nc_v4(frow + (int64_t)8 * p + (s0 + 2 * u) * 16 + 8 * t);
     }
+  }
+  uint2 t_lo = make_uint2(0u, 0u), t_hi = make_uint2(0u, 0u);
+  if (tail) {
+    t_lo = ldg_nc_v2(frow + (s1 - 1) * 16 + 4 * t);
+    t_hi = ldg_nc_v2(frow + (int64_t)8 * p + (s1 - 1) * 16 + 4 * t);
   }
   // ---- where this CTA's inputs and outputs live: index vectors are parameters too ----
   // plain contiguous input (no index, no scale): 8-byte copies after the wait; otherwise element by element
@@ -114,18 +125,26 @@ pass_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
   }
   __syncthreads();
 
-  // ---- lane (g, t) needs x[token g][k = 16 s + 4 t .. +3]; columns >= M re-read the last token ----
-  const __half* xrow = xs + min(g, M - 1) * xld + (b - b_first) * p + 4 * t;
+  // ---- tokens with the same k labelling; columns >= M re-read the last token ----
+  const __half* xrow = xs + min(g, M - 1) * xld + (b - b_first) * p;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int s = 0; s < FT_STEPS; ++s) {
-    if (live && s0 + s < s1) {
-      const uint2 v = *reinterpret_cast<const uint2*>(xrow + (s0 + s) * 16);
-      const uint32_t bfrag[2] = {v.x, v.y};
-      // k relabelled so that a lane's four consecutive k are MMA slots (2t, 2t+1, 2t+8, 2t+9) on both operands
-      const uint32_t a[4] = {a_lo[s].x, a_hi[s].x, a_lo[s].y, a_hi[s].y};
-      mma16816(acc, a, bfrag);
+  for (int u = 0; u < FT_PAIRS; ++u) {
+    if (u < npair) {
+      const uint4 v = *reinterpret_cast<const uint4*>(xrow + (s0 + 2 * u) * 16 + 8 * t);
+      const uint32_t b0[2] = {v.x, v.y}, b1[2] = {v.z, v.w};
+      // a lane's four consecutive k are MMA slots (2t, 2t+1, 2t+8, 2t+9) on both operands
+      const uint32_t a0[4] = {a_lo[u].x, a_hi[u].x, a_lo[u].y, a_hi[u].y};
+      const uint32_t a1[4] = {a_lo[u].z, a_hi[u].z, a_lo[u].w, a_hi[u].w};
+      mma16816(acc, a0, b0);
+      mma16816(acc, a1, b1);
     }
+  }
+  if (tail) {
+    const uint2 v = *reinterpret_cast<const uint2*>(xrow + (s1 - 1) * 16 + 4 * t);
+    const uint32_t bfrag[2] = {v.x, v.y};
+    const uint32_t a[4] = {t_lo.x, t_hi.x, t_lo.y, t_hi.y};
+    mma16816(acc, a, bfrag);
   }
 
   // ---- sum the k parts in a fixed order, store rows g / g+8 for tokens 2t, 2t+1 ----
@@ -189,16 +208,17 @@ gather_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, in
 int launch_pdl(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args);   // api.cu
 
 bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n) {
-  return M <= 8 && ps->p % 16 == 0 && ps->p >= 16 && (n % 4 == 0) && (((uintptr_t)ps->factors) & 7) == 0;
+  return M <= 8 && ps->p % 16 == 0 && ps->p >= 16 && (n % 8 == 0) && (((uintptr_t)ps->factors) & 15) == 0;
 }
 
 int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
                 const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s) {
   const int p = ps->p, ksteps = p / 16;
   int kparts = 1;
-  while (kparts < FT_WARPS && ceil_div(ksteps, kparts) > FT_STEPS) kparts *= 2;
+  while (kparts < FT_WARPS && ((ceil_div(ksteps, kparts) + 1) & ~1) > FT_STEPS) kparts *= 2;
   QUIP_CHECK_ARG(ceil_div(ksteps, kparts) <= FT_STEPS, "few-token pass: block size %d too large", p);
-  const int steps_per_part = ceil_div(ksteps, kparts);
+  int steps_per_part = ceil_div(ksteps, kparts);
+  if (kparts > 1) steps_per_part = (steps_per_part + 1) & ~1;          // parts start on a 32-wide k block
   const int rtiles = p / 16;
   const int64_t groups = (int64_t)ps->nblk * rtiles;
   const int per_cta = FT_WARPS / kparts;
