@@ -184,3 +184,22 @@ def test_abi_v2_structs_carry_the_optional_pointers():
     assert not s.inv_idx and not s.passes[0].factors_frag          # NULL by default: the C side takes the unfused routes
     hdr = open(os.path.join(ROOT, 'include', 'quip_b200.h')).read()
     assert 'QUIP_ABI_VERSION 2' in hdr and 'factors_frag' in hdr and 'inv_idx' in hdr
+
+
+def test_committed_bench_line_has_the_contract_keys():
+    """profiles/bench_r01_final.json is the JSON line bench.py printed on the B200: every key the driver reads is there."""
+    import json
+    path = os.path.join(ROOT, 'profiles', 'bench_r01_final.json')
+    line = [l for l in open(path).read().splitlines() if l.strip().startswith('{')][-1]
+    d = json.loads(line)
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline'):
+        assert k in d, k
+    assert d['warmup'] >= 3 and d['higher_is_better'] is True and d['scaling'] == 'weak' and d['vs_baseline'] is None
+    assert 'workload' in d['config'] and 'l2' in d['config'] and 'model' not in d['config']
+    assert set(d['e2e']) >= {'value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step'} and d['e2e']['h2d_bytes_per_step'] > 0
+    r = d['roofline']
+    assert r['bound'] in ('hbm', 'tensor') and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-9 and 0 < r['frac'] <= 1
+    assert set(d['cpu_baseline']) >= {'value', 'unit', 'cores', 'kind', 'sample'} and d['cpu_baseline']['kind'] in ('port', 'reference')
+    assert d['gpu_launches'] > 0 and {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(d['clocks'])
+    assert abs(d['value'] - d['n_gpus'] * d['steps'] * 2048 / (d['ms_per_step'] * d['steps'] / 1e3)) / d['value'] < 1e-6
