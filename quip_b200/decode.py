@@ -162,3 +162,22 @@ def graph_decode_benchmark(model, input_ids, max_len=None, check=False):
             tot += float(F.cross_entropy(logits.float(), ids[i + 1:i + 2]))
     ppl = float(np.exp(tot / (ids.numel() - 1))) if check else None
     return float(np.median(times)), ppl
+
+
+def graph_decode_throughput(model, batch, steps=32, max_len=64, seed=0):
+    """Aggregate tokens/s of `steps` graph-replayed decode steps with `batch` independent sequences (random token ids)."""
+    dev = next(iter(model.parameters())).device
+    dec = GraphDecoder(model, max_len=max_len, batch=batch).capture()
+    gen = torch.Generator().manual_seed(seed)
+    ids = torch.randint(0, model.config.vocab_size, (steps + 2, batch), generator=gen).to(dev)
+    for i in range(2):
+        dec.step(ids[i])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        dec.step(ids[2 + i])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return batch * 1e3 / ms, ms

@@ -47,3 +47,18 @@ def test_graph_decode_benchmark_reports_time_and_ppl():
     sec, ppl = graph_decode_benchmark(model, ids, check=True)
     sec0, ppl0 = decode_benchmark(model, ids, check=True)
     assert sec > 0 and abs(ppl - ppl0) / ppl0 < 2e-2
+
+
+def test_graph_decoder_batch_rows_are_independent_sequences():
+    from quip_b200.decode import GraphDecoder
+    model = _tiny_llama(4)
+    ids = torch.randint(0, 320, (3, 10), generator=torch.Generator().manual_seed(8)).cuda()
+    with torch.no_grad():
+        batched = GraphDecoder(model, max_len=16, batch=3).capture()
+        got = [batched.step(ids[:, i]).float().clone() for i in range(ids.shape[1])]
+        for b in range(3):
+            single = GraphDecoder(model, max_len=16, batch=1).capture()
+            for i in range(ids.shape[1]):
+                want = single.step(ids[b, i:i + 1])[0].float()
+                err = float((got[i][b] - want).norm() / want.norm())
+                assert err < 5e-3, (b, i, err)        # 3 tokens take the int8 two-tile route, 1 token the one-tile route
