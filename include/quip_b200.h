@@ -134,8 +134,16 @@ int quip_timing_enable(int on);
 int quip_timing_reset(void);
 int quip_timing_read(int path, double* total_ms, int64_t* launches, double* flops, double* bytes);
 
-/* Tuning knobs for ablations: "tc2" / "ts" = 1 route contractions with M > 128 to the 2-CTA / TS-mode tcgen05
- * kernels; "gather_rows", "pass_min_tiles" tune the un-projection kernels. */
+/* Routing switches for ablations, tests and micro-benchmarks (defaults in parentheses); results do not depend on them.
+ *   "side_fused" (1)  M > 8: a whole incoherence side in one kernel when both blocks are 32/64 wide and factors_frag is set
+ *   "fewtok" (1)      M <= 8: few-token pass / gather kernels (fused input gather, output scatter + bias)
+ *   "pdl" (1)         programmatic dependent launch along the few-token chain
+ *   "gemv" (1)        M <= 8: whole-K qgemv kernels (0: split-K mma.sync kernel)
+ *   "gv_int" (1)      qgemv: int8 tensor-core path for 2-/4-bit and <= 5 tokens (0: fp16 path)
+ *   "gv_tma" (1), "gv_cw" (16), "gv_rbc" (0 = auto), "gv_persist" (1)   variants of the cooperative int8 kernel
+ *   "gv_stream" (32)  streaming int8 kernel when N/16 >= value * SMs (0: never)
+ *   "tc2" / "ts" (0)  route contractions with M > 128 to the 2-CTA / TS-mode tcgen05 kernels
+ *   "gather_rows", "pass_min_tiles"   tune the many-token un-projection kernels */
 int quip_config(const char* key, int value);
 
 const char* quip_last_error(void);
