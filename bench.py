@@ -48,17 +48,27 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe: -lms 200).  The process is
+    started BEFORE the warm-up steps -- nvidia-smi's own start-up (NVML init under the driver lock) slowed the first
+    timed steps by ~25 % whenever it coincided with them -- and only the rows that arrive between mark_start() and
+    mark_end() are summarised."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.all_rows, self.t0, self.t1 = [], None, None
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), f'--query-gpu={self.Q}',
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -68,7 +78,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.all_rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -81,6 +91,9 @@ class ClockSampler:
         return False
 
     def summary(self):
+        t0 = self.t0 if self.t0 is not None else 0.0
+        t1 = (self.t1 if self.t1 is not None else time.perf_counter()) + 0.25
+        self.rows = [r for (ts, r) in self.all_rows if t0 <= ts <= t1] or [r for (_, r) in self.all_rows[-2:]]
         sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit())
         if not sm:
             return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
@@ -199,6 +212,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--layers', type=int, default=N_LAYERS, help=argparse.SUPPRESS)   # debugging only
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-decode', action='store_true', help='skip the one-token decode legs (quick runs)')
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -266,27 +280,29 @@ def main():
         return ms
 
     # ---- device-resident timing ----
-    with torch.no_grad():
+    with torch.no_grad(), ClockSampler(local) as clk:
         for i in range(a.warmup):
             evalloop.sample_nll(model, evalloop.LLAMA, ids_dev[i])
         barrier()
         launches0 = lib.quip_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         profiling = os.environ.get('QUIP_PROFILE') == '1'     # ncu --profile-from-start off: timed region only
-        with ClockSampler(local) as clk:
-            barrier()
-            if profiling:
-                torch.cuda.profiler.start()
-            e0.record()
-            nll = torch.zeros((), device=dev)
-            for i in range(a.warmup, total):
-                nll += evalloop.sample_nll(model, evalloop.LLAMA, ids_dev[i])
-            if world > 1:
-                dist.all_reduce(nll)
-            e1.record()
-            barrier()
-            if profiling:
-                torch.cuda.profiler.stop()
+        barrier()
+        if profiling:
+            torch.cuda.profiler.start()
+        clk.mark_start()
+        e0.record()
+        nll = torch.zeros((), device=dev)
+        for i in range(a.warmup, total):
+            nll += evalloop.sample_nll(model, evalloop.LLAMA, ids_dev[i])
+        if world > 1:
+            dist.all_reduce(nll)
+        e1.record()
+        barrier()
+        clk.mark_end()
+        if profiling:
+            torch.cuda.profiler.stop()
+    with torch.no_grad():
         ms = max_over_ranks(e0.elapsed_time(e1))
         launches = lib.quip_launch_count() - launches0
 
@@ -356,7 +372,7 @@ def main():
                                           '(sibling-stream overlap off, %.2f ms/step); the headline timed region runs '
                                           'with the overlap on' % (serial_ms / a.steps)), peak_source=pk['source'] + ', sustained bf16 (kernel timed inside a long step)'),
                clocks=clk.summary())
-    if world == 1:
+    if world == 1 and not a.no_decode:
         try:
             for g in groups:
                 g.dissolve()
