@@ -25,11 +25,16 @@
 //       y[m][n] = scales_n (A1 (acc - T_m) + A2 S_m) - zeros_n S_m + bias_n,
 //       (A1, A2) = (64, 0) / (8, 3.5) / (256, 0) for 2 / 3 / 4 bits.
 //
-// Skeleton.  A CTA owns RBC row blocks over the *whole* K (8 warps split the k super-blocks), so the only
-// reduction is through shared memory (one barrier per tile, double-buffered): no split-K partials,
-// counters or fences.  The packed words of the first D steps are requested before anything else (they do
-// not depend on the previous kernel: with programmatic dependent launch they are in flight while it
-// drains), then the tokens are staged, then a D-deep register ring keeps D x RBC x 512 B per warp in flight.
+// Skeleton.  A CTA owns RBC row blocks over the *whole* K (its warps split the k super-blocks), so the only
+// reduction is through shared memory: no split-K partials, counters or fences.  The packed words are
+// requested before anything else (they do not depend on the previous kernel: with programmatic dependent
+// launch they are in flight while it drains), then the tokens are staged.
+//
+// Three kernels carry the int8 datapath, one per regime (routing in qgemv() below):
+//   qgemv_i8_tma_kernel     a single layer (all latency): bulk-copy ring + consumer warps + epilogue warp
+//   qgemv_i8_kernel         its register-ring (LDG) sibling, used when K x tokens leaves no room for the ring
+//   qgemv_i8_stream_kernel  >= 32 row blocks per SM (stacked / grouped matrices): barrier-free streaming,
+//                           78 % of the HBM peak at one token
 #include "tc_common.cuh"
 
 namespace quip {
