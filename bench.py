@@ -223,7 +223,8 @@ def main():
                             parallelism=f'dp{a.gpus}', l2='inputs larger than L2: each step streams 3.5 GB of packed '
                                                           'weights + butterfly factors',
                             setup='descriptors, fragment-order factor copies and per-stream workspaces are built by two '
-                                  'untimed priming passes before the W warm-up steps'))
+                                  'untimed priming passes before the W warm-up steps; the decoder stack of a step is then '
+                                  'captured once in a CUDA graph and replayed (QUIP_NO_GRAPH=1 for eager launches)'))
 
     if a.impl == 'reference':
         if rank != 0:
@@ -262,6 +263,16 @@ def main():
         for _ in range(2):
             evalloop.sample_nll(model, evalloop.LLAMA, prime)
     torch.cuda.synchronize()
+    # the decoder stack of a step as one CUDA graph (QUIP_NO_GRAPH=1: eager launches, as the roofline replay leg uses)
+    stepper = None
+    if os.environ.get('QUIP_NO_GRAPH') != '1':
+        try:
+            stepper = evalloop.enable_graphed_eval(model, evalloop.LLAMA, prime)
+        except Exception as e:
+            print(f'bench: graph capture failed ({e!r}); falling back to eager launches', file=sys.stderr)
+            model._quip_graph_step = None
+            stepper = None
+    step_fn = stepper if stepper is not None else (lambda ids: evalloop.sample_nll(model, evalloop.LLAMA, ids))
     gen = torch.Generator().manual_seed(1234 + rank)
     total = a.warmup + a.steps
     ids_host = torch.randint(0, cfg.vocab_size, (total, 1, SEQ), generator=gen).pin_memory()
@@ -282,7 +293,7 @@ def main():
     # ---- device-resident timing ----
     with torch.no_grad(), ClockSampler(local) as clk:
         for i in range(a.warmup):
-            evalloop.sample_nll(model, evalloop.LLAMA, ids_dev[i])
+            step_fn(ids_dev[i])
         barrier()
         launches0 = lib.quip_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -294,7 +305,7 @@ def main():
         e0.record()
         nll = torch.zeros((), device=dev)
         for i in range(a.warmup, total):
-            nll += evalloop.sample_nll(model, evalloop.LLAMA, ids_dev[i])
+            nll += step_fn(ids_dev[i])
         if world > 1:
             dist.all_reduce(nll)
         e1.record()
@@ -304,7 +315,7 @@ def main():
             torch.cuda.profiler.stop()
     with torch.no_grad():
         ms = max_over_ranks(e0.elapsed_time(e1))
-        launches = lib.quip_launch_count() - launches0
+        launches = lib.quip_launch_count() - launches0       # eager launches; a replayed graph is counted below
 
         # ---- roofline leg: per-launch CUDA-event timing of the dominant kernel over the same K steps.  The
         # sibling overlap is switched off for this replay: concurrent kernels share the SMs, so a per-launch
@@ -321,6 +332,9 @@ def main():
         r1.record()
         barrier()
         serial_ms = r0.elapsed_time(r1)
+        if stepper is not None:
+            # the graph replays exactly the launches of an eager step: count them from this eager replay of the same K steps
+            launches = lib.quip_launch_count() - launches0 - launches
         lib.quip_timing_enable(0)
         tms, tn, tfl, tby = C.c_double(), C.c_int64(), C.c_double(), C.c_double()
         _lib.check(lib.quip_timing_read(2, C.byref(tms), C.byref(tn), C.byref(tfl), C.byref(tby)))

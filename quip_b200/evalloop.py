@@ -130,6 +130,53 @@ def sample_nll(model, arch: Arch, batch, layer_range=None):
     return sample_logits_nll(model, arch, h, batch, model.seqlen)
 
 
+class GraphedSampleNLL:
+    """`sample_nll` for samples of one fixed length with the decoder stack, final norm, lm_head and loss replayed from
+    one CUDA graph.  A 7B step is ~1900 kernel launches; issued eagerly they keep a host core busy for most of the step,
+    and four ranks on a host with few cores run four times slower each.  The embedding / mask / rotary front end
+    (`layer_inputs`, a handful of kernels) stays eager; its layer kwargs are the same for every sample of that length."""
+
+    def __init__(self, model, arch: Arch, example_batch):
+        self.model, self.arch = model, arch
+        dev = example_batch.device
+        with torch.no_grad():
+            h, kw = layer_inputs(model, arch, example_batch)
+        self.h, self.kw, self.labels = h.clone(), kw, example_batch.clone()
+        self.shape = tuple(example_batch.shape)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(2):                              # lazy set-up (descriptors, workspaces) outside the graph
+                self._body()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.out = self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+
+    def _body(self):
+        h = self.h
+        for layer in self.arch.layers(self.model):
+            h = _call_layer(layer, h, self.kw)
+        return sample_logits_nll(self.model, self.arch, h, self.labels, self.model.seqlen)
+
+    @torch.no_grad()
+    def __call__(self, batch):
+        if tuple(batch.shape) != self.shape:
+            raise ValueError(f'graph was captured for samples of shape {self.shape}, got {tuple(batch.shape)}')
+        h, _ = layer_inputs(self.model, self.arch, batch)
+        self.h.copy_(h)
+        self.labels.copy_(batch)
+        self.graph.replay()
+        return self.out.clone()
+
+
+def enable_graphed_eval(model, arch: Arch, example_batch):
+    """Capture once; `eval_ppl` then replays the graph for every resident, same-length sample.  Returns the stepper
+    (also callable directly: nll = stepper(ids))."""
+    model._quip_graph_step = GraphedSampleNLL(model, arch, example_batch)
+    return model._quip_graph_step
+
+
 @torch.no_grad()
 def eval_ppl(model, arch: Arch, testenc, dev, sample_ids: Optional[List[int]] = None, offload=False,
              verbose=True, reduce_fn=None):
@@ -149,6 +196,20 @@ def eval_ppl(model, arch: Arch, testenc, dev, sample_ids: Optional[List[int]] = 
         for mod in arch.pre(model):
             mod.to(dev)
         layers[0].to(dev)
+    stepper = getattr(model, '_quip_graph_step', None)
+    if stepper is not None and not offload and stepper.shape == (1, seqlen):
+        # sample-major through the captured graph: same numbers, no per-kernel host work
+        nll = torch.zeros((), dtype=torch.float32, device=dev)
+        for i in mine:
+            nll += stepper(ids[:, i * seqlen:(i + 1) * seqlen].to(dev, non_blocking=True))
+        count = torch.tensor(float(len(mine) * seqlen), device=dev)
+        if reduce_fn is not None:
+            nll, count = reduce_fn(nll, count)
+        ppl = torch.exp(nll / count).item()
+        if verbose:
+            print(ppl)
+        model.config.use_cache = use_cache
+        return ppl
     dtype = next(iter(model.parameters())).dtype
     inps = torch.zeros((len(mine), seqlen, model.config.hidden_size), dtype=dtype, device=dev)
     kw = {}

@@ -288,6 +288,9 @@ class SiblingGroup:
             if self.streams is None or self.streams[0].device != dev:
                 self.streams = [torch.cuda.Stream(device=dev) for _ in self.members[1:]]
             cur = torch.cuda.current_stream(dev)
+            # inside a CUDA-graph capture the allocator's blocks are reused in stream order within the graph, and every
+            # side stream starts behind `ready`: no record_stream there (it is an eager-mode allocator hint)
+            capturing = torch.cuda.is_current_stream_capturing()
             ready = torch.cuda.Event()
             ready.record(cur)
             order = [index] + [j for j in range(len(self.members)) if j != index]
@@ -302,7 +305,8 @@ class SiblingGroup:
                     y = self.members[j]._forward_impl(x)
                     ev = torch.cuda.Event()
                     ev.record(st)
-                x.record_stream(st)
+                if not capturing:
+                    x.record_stream(st)
                 self._outs[j], self._events[j] = y, ev
             self._key = key
         y, ev = self._outs[index], self._events[index]
@@ -310,7 +314,8 @@ class SiblingGroup:
         if ev is not None:
             cur = torch.cuda.current_stream(x.device)
             cur.wait_event(ev)
-            y.record_stream(cur)
+            if not torch.cuda.is_current_stream_capturing():
+                y.record_stream(cur)
         return y
 
 

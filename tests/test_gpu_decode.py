@@ -62,3 +62,26 @@ def test_graph_decoder_batch_rows_are_independent_sequences():
                 want = single.step(ids[b, i:i + 1])[0].float()
                 err = float((got[i][b] - want).norm() / want.norm())
                 assert err < 5e-3, (b, i, err)        # 3 tokens take the int8 two-tile route, 1 token the one-tile route
+
+
+def test_graphed_sample_nll_equals_eager_and_feeds_eval_ppl():
+    """The decoder stack + head + loss of a fixed-length sample replayed from one CUDA graph (evalloop.GraphedSampleNLL),
+    with the q/k/v and gate/up sibling groups on their side streams inside the capture."""
+    from quip_b200 import evalloop
+    from quip_b200.quant import group_siblings
+    model = _tiny_llama(4)
+    group_siblings(model)
+    ids = torch.randint(0, 320, (4, 1, 64), generator=torch.Generator().manual_seed(9)).cuda()
+    with torch.no_grad():
+        eager = [float(evalloop.sample_nll(model, evalloop.LLAMA, ids[i])) for i in range(4)]
+        stepper = evalloop.enable_graphed_eval(model, evalloop.LLAMA, ids[0])
+        graphed = [float(stepper(ids[i])) for i in range(4)]
+    for e, g in zip(eager, graphed):
+        assert abs(e - g) <= 1e-4 * abs(e), (e, g)
+    flat = ids.reshape(1, -1)
+    ppl_graph = evalloop.eval_ppl(model, evalloop.LLAMA, flat, torch.device('cuda:0'), verbose=False)
+    model._quip_graph_step = None
+    ppl_eager = evalloop.eval_ppl(model, evalloop.LLAMA, flat, torch.device('cuda:0'), verbose=False)
+    assert abs(ppl_graph - ppl_eager) <= 1e-3 * ppl_eager
+    with pytest.raises(ValueError):
+        stepper(ids[0][:, :32])
