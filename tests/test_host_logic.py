@@ -203,3 +203,19 @@ def test_committed_bench_line_has_the_contract_keys():
     assert set(d['cpu_baseline']) >= {'value', 'unit', 'cores', 'kind', 'sample'} and d['cpu_baseline']['kind'] in ('port', 'reference')
     assert d['gpu_launches'] > 0 and {'sm_mhz', 'sm_max_mhz', 'reasons'} <= set(d['clocks'])
     assert abs(d['value'] - d['n_gpus'] * d['steps'] * 2048 / (d['ms_per_step'] * d['steps'] / 1e3)) / d['value'] < 1e-6
+
+
+def test_clock_sampler_summarises_only_rows_inside_the_timed_region():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    clk = bench.ClockSampler(0)
+    row = lambda mhz, cap: [str(mhz), '1965', '700.0', 'Not Active', 'Not Active', 'Not Active', cap]
+    clk.all_rows = [(1.0, row(1200, 'Not Active')), (5.0, row(1950, 'Active')), (5.2, row(1965, 'Not Active')),
+                    (9.0, row(900, 'Not Active'))]
+    clk.t0, clk.t1 = 4.9, 5.3
+    s = clk.summary()
+    assert s['samples'] == 2 and s['sm_mhz'] == 1965.0 and s['sm_max_mhz'] == 1965.0 and s['reasons'] == ['sw_power_cap']
+    clk.t0, clk.t1 = 20.0, 21.0                       # nothing landed inside: fall back to the last rows, never crash
+    assert clk.summary()['samples'] == 2
