@@ -1,0 +1,133 @@
+"""The producer side (quip_b200/quantize.py: calibration Hessian, random butterflies, LDLQ, LayerParts) on the CPU, against
+the oracle's restatements of the reference (oracle/ldlq.py, oracle/quantflow.py, oracle/butterfly.py, oracle/forward.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+from oracle import butterfly as obf
+from oracle import forward as ofw
+from oracle import ldlq as oldlq
+from oracle import quantflow as oqf
+from quip_b200 import quantize as qz
+
+
+def _np_bpp(b):
+    return ([b.B0.numpy(), b.B1.numpy()], b.p_in.numpy(), b.p_out.numpy())
+
+
+@pytest.mark.parametrize('n,mode', [(96, 'blocked'), (128, 'kron'), (384, 'noperm'), (640, 'blocked')])
+def test_butterfly_apply_matches_reference_structure(n, mode):
+    g = torch.Generator().manual_seed(n)
+    b = qz.random_butterfly(n, mode, g)
+    x = torch.randn(n, 5, generator=g)
+    want = obf.mul_butterfly(_np_bpp(b), x.numpy())                        # method.py:46-67 restated
+    np.testing.assert_allclose(qz.butterfly_apply(b, x).numpy(), want, rtol=0, atol=3e-5)
+    back = qz.butterfly_apply_t(b, qz.butterfly_apply(b, x))               # orthogonal: M^T M = I
+    np.testing.assert_allclose(back.numpy(), x.numpy(), atol=3e-5)
+    D = qz.butterfly_apply(b, torch.eye(n))
+    np.testing.assert_allclose((D @ D.T).numpy(), np.eye(n), atol=3e-5)
+    if mode == 'kron':
+        assert b.B0.shape[0] == 1 and b.B1.shape[0] == 1
+    if mode == 'noperm':
+        assert torch.equal(b.p_in, torch.arange(n))
+
+
+def test_blocked_ldlq_agrees_with_the_sequential_oracle():
+    z = np.load(os.path.join(GOLDEN, 'ldlq.npz'))
+    for case in z['cases']:
+        key, nbits, npasses = str(case).split(':')
+        ci, meth = key.split('_')
+        w, H = torch.from_numpy(z[f'{ci}_w']), torch.from_numpy(z[f'{ci}_H'])
+        fn = qz.ldlq_round if meth == 'ldlq' else qz.ldlq_rg_round
+        for block in (32, 1024):
+            got = fn(w, H, int(nbits), int(npasses), block=block)
+            want = torch.from_numpy(z[f'{key}_out'])                      # the live reference's codes
+            assert float((got == want).float().mean()) > 0.995, (case, block)
+            loss = lambda q: float(torch.trace((q - w) @ H @ (q - w).T))
+            assert loss(got) < 1.005 * loss(want), (case, block)
+
+
+def test_hessian_accumulator_matches_reference_semantics():
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randn(2, 40, 64, generator=g).half(), torch.randn(1, 40, 64, generator=g).half()]
+    acc = qz.HessianAccumulator(64)
+    for x in xs:
+        acc.add_batch(x)
+    H, n = oqf.accumulate_hessian(xs)
+    assert acc.batches == n == 3                                            # batches, not tokens (method.py:105,118)
+    np.testing.assert_allclose(acc.result().numpy(), oqf.finalize_hessian(H, n).numpy(), rtol=1e-6)
+
+
+@pytest.mark.parametrize('bits,method,qfn,incoh,rescale', [(2, 'ldlq', 'b', 'blocked', True), (2, 'ldlqRG', 'b', 'kron', True),
+                                                           (4, 'ldlq', 'a', None, False), (3, 'ldlq', 'a', 'noperm', True)])
+def test_quantize_linear_parts_are_consistent_and_better_than_nearest(bits, method, qfn, incoh, rescale):
+    g = torch.Generator().manual_seed(bits * 7 + len(method))
+    N, K = 96, 128
+    W0 = (torch.randn(N, K, generator=g) * 0.05).half()
+    W0[:, 3] *= 8                                                            # an outlier column: what incoherence spreads out
+    X = (torch.randn(1, 512, K, generator=g) * (1 + 3 * torch.rand(K, generator=g))).half()
+    acc = qz.HessianAccumulator(K)
+    acc.add_batch(X)
+    H = acc.result()
+    bias = torch.randn(N, generator=g).half()
+    parts, W_hat = qz.quantize_linear(W0, H, bits=bits, method=method, greedy_passes=1, qfn=qfn, rescale=rescale, incoh=incoh,
+                                      bias=bias, generator=g, return_dense=True)
+    assert parts.codes.dtype == torch.uint8 and int(parts.codes.max()) <= 2 ** bits - 1
+    # the parts describe the same matrix as the dense fake-quantised weight (reference postproc, method.py:195-214)
+    pn = dict(bits=bits, qfn=qfn, codes=parts.codes.numpy(), scales=parts.scales.numpy(), zeros=parts.zeros.numpy(),
+              bias=bias.numpy(), scaleWH=None if parts.scaleWH is None else parts.scaleWH.numpy(),
+              U=None if parts.U is None else _np_bpp(parts.U), V=None if parts.V is None else _np_bpp(parts.V))
+    W_ref = ofw.w_ref(pn)
+    assert np.mean(W_ref.view(np.uint16) == W_hat.numpy().view(np.uint16)) > 0.98
+    np.testing.assert_allclose(W_ref.astype(np.float32), W_hat.float().numpy(), atol=2e-3 * float(W0.abs().max()))
+    # ... and the kernel-side plan of those parts reproduces the dense forward within the path's tolerance
+    x = (torch.randn(6, K, generator=g) * (1 + 3 * torch.rand(K, generator=g))).half().numpy()
+    y_dense = ofw.dense_forward(x, W_ref, bias.numpy())
+    y_kernel = ofw.kernel_forward(x, pn)
+    assert ofw.rel_err(y_kernel, y_dense) < 1e-3
+    # adaptive rounding beats nearest rounding on the same grid in the proxy loss
+    loss = qz.proxy_loss(W_hat.float(), W0.float(), H)
+    assert loss < {2: 0.35, 3: 0.08, 4: 0.02}[bits], loss
+
+
+def test_quantized_parts_pack_on_the_host_and_round_trip():
+    from quip_b200 import quant as Q
+    g = torch.Generator().manual_seed(4)
+    W0 = (torch.randn(64, 128, generator=g) * 0.05).half()
+    acc = qz.HessianAccumulator(128)
+    acc.add_batch((torch.randn(1, 300, 128, generator=g)).half())
+    parts = qz.quantize_linear(W0, acc.result(), bits=2, qfn='b', incoh='blocked', generator=g)
+    ql = Q.QuantLinear(infeatures=128, outfeatures=64, **Q.spec_from_parts(parts))
+    ql.pack_parts(parts)
+    assert ql.qweight.dtype == torch.int32 and ql.qweight.numel() == Q.packed_words(64, 128, 2)
+    plan_codes = Q.unpack_codes(ql.qweight, 64, 128, 2)
+    assert sorted(np.bincount(plan_codes.numpy().ravel(), minlength=4)) == sorted(np.bincount(parts.codes.numpy().ravel(), minlength=4))
+
+
+def test_quantize_model_walks_the_decoder_stack():
+    """Tiny random OPT on the CPU: every decoder Linear gets parts, the fake-quantised model stays close to the original, and
+    the 4-bit quantisation is closer than the 2-bit one."""
+    from transformers import OPTConfig, OPTForCausalLM
+    from quip_b200 import evalloop
+    cfg = OPTConfig(hidden_size=128, ffn_dim=256, num_hidden_layers=2, num_attention_heads=4, vocab_size=256,
+                    max_position_embeddings=64, word_embed_proj_dim=128)
+    torch.manual_seed(0)
+    ref = OPTForCausalLM(cfg).float().eval()
+    ref.seqlen = 32
+    ids = [torch.randint(0, 256, (1, 32), generator=torch.Generator().manual_seed(i)) for i in range(6)]
+    with torch.no_grad():
+        base = ref(ids[0]).logits
+    errs = {}
+    for bits in (2, 4):
+        import copy
+        m = copy.deepcopy(ref)
+        parts = qz.quantize_model(m, evalloop.OPT, ids, bits=bits, method='ldlq', qfn='b', rescale=True, incoh='blocked',
+                                  generator=torch.Generator().manual_seed(1), pack=False)
+        assert len(parts) == 2 * 6 and all(k.startswith('model.decoder.layers.') for k in parts)
+        assert parts['model.decoder.layers.1.fc1'].codes.shape == (256, 128)
+        with torch.no_grad():
+            errs[bits] = float((m(ids[0]).logits - base).norm() / base.norm())
+    assert errs[4] < errs[2] and errs[4] < 0.2, errs
