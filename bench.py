@@ -144,7 +144,7 @@ def decode_leg(model, dev, pk):
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph, stream=side):
+            with torch.cuda.graph(graph, stream=side, capture_error_mode='thread_local'):
                 step()
         torch.cuda.current_stream().wait_stream(side)
         graph.replay()

@@ -121,7 +121,7 @@ class GraphDecoder:
                 self._step()
             self.position.copy_(pos0)
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=side):
+            with torch.cuda.graph(self.graph, stream=side, capture_error_mode='thread_local'):
                 self._step()
         torch.cuda.current_stream(self.dev).wait_stream(side)
         self.position.copy_(pos0)

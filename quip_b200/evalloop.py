@@ -149,7 +149,7 @@ class GraphedSampleNLL:
             for _ in range(2):                              # lazy set-up (descriptors, workspaces) outside the graph
                 self._body()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, stream=side):
+            with torch.cuda.graph(self.graph, stream=side, capture_error_mode='thread_local'):
                 self.out = self._body()
         torch.cuda.current_stream(dev).wait_stream(side)
 
