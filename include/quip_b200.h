@@ -115,6 +115,21 @@ int quip_gather(const void* in, void* out, int64_t M, int32_t n, const int32_t* 
 int quip_rot_pass(const QuipPass* pass, const void* in, void* out, int64_t M, int32_t n, int impl,
                   void* stream);
 
+/* Glue of a Llama decoder layer between its packed linears: what the reference's eval loop gets from the HF layer it
+ * calls (llama.py:227 `layer(inps[j].unsqueeze(0), attention_mask=..., position_ids=...)`: LlamaRMSNorm, the residual
+ * adds, apply_rotary_pos_emb, SiLU(gate)*up), each as one HBM pass with the HF modules' fp16 rounding points.  All
+ * tensors fp16, contiguous, 16-byte aligned.
+ *   quip_rmsnorm   s = x (+ residual);  y = weight * fp16(s * rsqrt(mean(s^2) + eps));  s is written to sum_out when
+ *                  given (residual and sum_out may be NULL; sum_out may alias x or residual).  d % 8 == 0, d <= 32768.
+ *   quip_rope      in place on q (rows, n_q_heads*head_dim) and k (rows, n_kv_heads*head_dim) with cos/sin
+ *                  (rows, head_dim): out = x*cos + rotate_half(x)*sin.  head_dim % 16 == 0; k may be NULL with 0 heads.
+ *   quip_silu_mul  out = silu(gate) * up over n elements (n % 8 == 0); out may alias gate or up. */
+int quip_rmsnorm(const void* x, const void* residual, const void* weight, void* sum_out, void* y,
+                 int64_t rows, int32_t d, float eps, void* stream);
+int quip_rope(void* q, void* k, const void* cos, const void* sin, int64_t rows, int32_t n_q_heads,
+              int32_t n_kv_heads, int32_t head_dim, void* stream);
+int quip_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream);
+
 /* codes (N,K) uint8 row-major <-> native packed layout.  Replaces Quant3Linear.pack (quant.py:185-220). */
 int quip_pack_codes(const uint8_t* codes_nk, int32_t N, int32_t K, int32_t bits, int32_t* qweight,
                     void* stream);

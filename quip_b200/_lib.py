@@ -44,6 +44,11 @@ EXPORTS = {
                               C.c_void_p]),
     'quip_rot_pass': (C.c_int, [C.POINTER(QuipPass), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int,
                                 C.c_void_p]),
+    'quip_rmsnorm': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_float,
+                               C.c_void_p]),
+    'quip_rope': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                            C.c_void_p]),
+    'quip_silu_mul': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
     'quip_pack_codes': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'quip_unpack_codes': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     'quip_convert_ref': (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),

@@ -108,6 +108,18 @@ def _call_layer(layer, h, kwargs):
     return out[0] if isinstance(out, (tuple, list)) else out
 
 
+def run_layers(model, arch: Arch, layers, h, kwargs):
+    """h through `layers` in order.  Llama layers on a CUDA device go through the fused stack (quip_b200/fused.py: the
+    glue between the linears as four kernels per layer) when QUIP_FUSED_LAYER=1; otherwise the HF layers are called."""
+    if arch.name == 'llama' and h.is_cuda:
+        from . import fused
+        if fused.enabled() and fused.supports(model, h, kwargs):
+            return fused.llama_stack(layers, h, kwargs)
+    for layer in layers:
+        h = _call_layer(layer, h, kwargs)
+    return h
+
+
 def sample_logits_nll(model, arch: Arch, h, labels, seqlen):
     """final norm -> lm_head -> shifted CE on fp16 logits, scaled by seqlen (opt.py:280-295)."""
     for mod in arch.post(model):
@@ -125,8 +137,7 @@ def sample_nll(model, arch: Arch, batch, layer_range=None):
     h, kw = layer_inputs(model, arch, batch)
     layers = arch.layers(model)
     lo, hi = layer_range or (0, len(layers))
-    for i in range(lo, hi):
-        h = _call_layer(layers[i], h, kw)
+    h = run_layers(model, arch, [layers[i] for i in range(lo, hi)], h, kw)
     return sample_logits_nll(model, arch, h, batch, model.seqlen)
 
 
@@ -154,9 +165,7 @@ class GraphedSampleNLL:
         torch.cuda.current_stream(dev).wait_stream(side)
 
     def _body(self):
-        h = self.h
-        for layer in self.arch.layers(self.model):
-            h = _call_layer(layer, h, self.kw)
+        h = run_layers(self.model, self.arch, list(self.arch.layers(self.model)), self.h, self.kw)
         return sample_logits_nll(self.model, self.arch, h, self.labels, self.model.seqlen)
 
     @torch.no_grad()

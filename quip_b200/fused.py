@@ -1,0 +1,137 @@
+"""Llama decoder layers of the eval loop with the glue between the packed linears fused (csrc/glue.cu).
+
+The reference's eval loop calls the HF decoder layer (llama.py:227); around the seven linears that layer issues ~25
+elementwise / reduction launches (LlamaRMSNorm 8, apply_rotary_pos_emb 9 for q and k, residual adds, SiLU and the gate
+product) which cost 27 % of a 2048-token step once the linears are packed (profiles/launches_r01.json).  `llama_stack`
+runs the same layers -- the layer's own modules for every linear and its own weights for the norms -- with that glue as
+four kernel launches per layer:
+
+    x        = rmsnorm(h)                                   first layer only
+    q, k, v  = q_proj(x), k_proj(x), v_proj(x);  rope_(q, k)           in place, token-major layout
+    o        = o_proj(SDPA(q, k, v))                        torch SDPA (cuDNN / flash), strided head views, no copies
+    h, x     = add_rmsnorm(h, o)                            residual add + post-attention norm
+    d        = down_proj(silu_mul(gate_proj(x), up_proj(x)))
+    h, x     = add_rmsnorm(h, d)                            residual add + the NEXT layer's input norm
+
+Every fp16 rounding point of the HF modules is kept (see glue.cu), so the hidden states differ from the HF layer's only
+through the summation order of the norms' fp32 mean.
+
+`ops` is the provider of the three glue kernels: `CudaGlue` (the product: the C ABI, CUDA only, raises without the
+extension) or, in the CPU tests, the torch restatement under oracle/ -- which this module never imports.
+"""
+import ctypes as C
+import os
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+
+class CudaGlue:
+    """quip_rmsnorm / quip_rope / quip_silu_mul of the C ABI on torch tensors (fp16, CUDA, contiguous)."""
+
+    @staticmethod
+    def _check(*ts):
+        for t in ts:
+            if t is None:
+                continue
+            if not t.is_cuda:
+                raise RuntimeError('the fused glue kernels run on a CUDA device only (there is no CPU fallback)')
+            if t.dtype != torch.float16 or not t.is_contiguous():
+                raise ValueError('fused glue kernels take contiguous fp16 tensors')
+
+    @staticmethod
+    def _stream(t):
+        return torch.cuda.current_stream(t.device).cuda_stream
+
+    def rmsnorm(self, x, weight, eps, residual=None):
+        """y = weight * norm(x [+ residual]).  Returns y, or (x + residual, y) when a residual is given."""
+        self._check(x, weight, residual)
+        d = x.shape[-1]
+        rows = x.numel() // d
+        y = torch.empty_like(x)
+        s = torch.empty_like(x) if residual is not None else None
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().quip_rmsnorm(x.data_ptr(), residual.data_ptr() if residual is not None else None,
+                                                weight.data_ptr(), s.data_ptr() if s is not None else None, y.data_ptr(),
+                                                rows, d, C.c_float(eps), self._stream(x)))
+        return y if residual is None else (s, y)
+
+    def rope_(self, q, k, cos, sin, head_dim):
+        """In place: q (..., nq*hd), k (..., nkv*hd) token-major; cos, sin (rows, hd)."""
+        self._check(q, k, cos, sin)
+        rows = q.numel() // q.shape[-1]
+        if cos.numel() != rows * head_dim or sin.numel() != rows * head_dim:
+            raise ValueError(f'cos/sin must hold one row of {head_dim} per token ({rows} tokens), got {tuple(cos.shape)}')
+        with torch.cuda.device(q.device):
+            _lib.check(_lib.load().quip_rope(q.data_ptr(), k.data_ptr(), cos.data_ptr(), sin.data_ptr(), rows,
+                                             q.shape[-1] // head_dim, k.shape[-1] // head_dim, head_dim, self._stream(q)))
+
+    def silu_mul(self, gate, up):
+        self._check(gate, up)
+        out = torch.empty_like(gate)
+        with torch.cuda.device(gate.device):
+            _lib.check(_lib.load().quip_silu_mul(gate.data_ptr(), up.data_ptr(), out.data_ptr(), gate.numel(),
+                                                 self._stream(gate)))
+        return out
+
+
+def enabled():
+    """The fused stack is opt-in (QUIP_FUSED_LAYER=1) until it has been measured on a B200."""
+    return os.environ.get('QUIP_FUSED_LAYER') == '1'
+
+
+def supports(model, h, kwargs):
+    """Llama-family model, one fp16 sample, SiLU MLP, HF default rotary application, SDPA attention."""
+    cfg = getattr(model, 'config', None)
+    if cfg is None or getattr(cfg, 'model_type', None) != 'llama':
+        return False
+    if getattr(cfg, 'hidden_act', 'silu') != 'silu' or getattr(cfg, '_attn_implementation', 'sdpa') not in ('sdpa', None):
+        return False
+    if h.dim() != 3 or h.shape[0] != 1 or h.dtype != torch.float16:
+        return False
+    pe = kwargs.get('position_embeddings')
+    if pe is None or pe[0].shape[0] != 1 or pe[0].dtype != torch.float16:
+        return False
+    hd = getattr(cfg, 'head_dim', None) or cfg.hidden_size // cfg.num_attention_heads
+    return hd % 16 == 0 and cfg.hidden_size % 8 == 0 and cfg.intermediate_size % 8 == 0
+
+
+def llama_stack(layers, h, kwargs, ops=None):
+    """`for layer in layers: h = layer(h, **kwargs)` for LlamaDecoderLayers on one sample h (1, S, hidden)."""
+    ops = ops or CudaGlue()
+    cos, sin = kwargs['position_embeddings']
+    cos, sin = cos[0].contiguous(), sin[0].contiguous()                     # (S, head_dim)
+    mask = kwargs.get('attention_mask')
+    S = h.shape[1]
+    pend = None                        # previous layer's MLP output, not yet added to h
+    x = None
+    h = h.contiguous()
+    for layer in layers:
+        a, mlp = layer.self_attn, layer.mlp
+        n1, n2 = layer.input_layernorm, layer.post_attention_layernorm
+        hd = a.head_dim
+        if pend is None:
+            x = ops.rmsnorm(h, n1.weight, n1.variance_epsilon)
+        else:
+            h, x = ops.rmsnorm(h, n1.weight, n1.variance_epsilon, residual=pend)
+        q, k, v = a.q_proj(x), a.k_proj(x), a.v_proj(x)                     # sibling groups launch these concurrently
+        ops.rope_(q, k, cos, sin, hd)
+        nq, nkv = q.shape[-1] // hd, k.shape[-1] // hd
+        qh = q.view(1, S, nq, hd).transpose(1, 2)
+        kh = k.view(1, S, nkv, hd).transpose(1, 2)
+        vh = v.view(1, S, nkv, hd).transpose(1, 2)
+        extra = {}
+        if nkv != nq:                                                       # as transformers' sdpa_attention_forward
+            if mask is None:
+                extra['enable_gqa'] = True
+            else:
+                kh = kh.repeat_interleave(nq // nkv, dim=1)
+                vh = vh.repeat_interleave(nq // nkv, dim=1)
+        o = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=mask, dropout_p=0.0, scale=a.scaling,
+                                           is_causal=(mask is None and S > 1), **extra)
+        o = o.transpose(1, 2).reshape(1, S, nq * hd).contiguous()
+        h, x = ops.rmsnorm(h, n2.weight, n2.variance_epsilon, residual=a.o_proj(o))
+        pend = mlp.down_proj(ops.silu_mul(mlp.gate_proj(x), mlp.up_proj(x)))
+    return h if pend is None else h + pend

@@ -1,0 +1,93 @@
+"""CPU tests of the fused Llama stack's host logic (quip_b200/fused.py) with the glue ops injected from oracle/glue.py,
+against the HF decoder layers themselves."""
+import pytest
+import torch
+
+from oracle.glue import TorchGlue
+from quip_b200 import evalloop, fused
+
+
+def _tiny(dtype, nkv=4, layers=3):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    cfg = LlamaConfig(hidden_size=128, intermediate_size=352, num_hidden_layers=layers, num_attention_heads=4,
+                      num_key_value_heads=nkv, vocab_size=199, max_position_embeddings=64)
+    torch.manual_seed(0)
+    m = LlamaForCausalLM(cfg).to(dtype).eval()
+    m.seqlen = 32
+    return m
+
+
+@pytest.mark.parametrize('dtype,nkv', [(torch.float32, 4), (torch.float32, 2), (torch.float16, 4)])
+def test_stack_with_torch_glue_equals_hf_layers(dtype, nkv):
+    m = _tiny(dtype, nkv)
+    ids = torch.randint(0, 199, (1, 32), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        h, kw = evalloop.layer_inputs(m, evalloop.LLAMA, ids)
+        ref = h
+        for layer in m.model.layers:
+            ref = evalloop._call_layer(layer, ref, kw)
+        got = fused.llama_stack(list(m.model.layers), h.clone(), kw, ops=TorchGlue())
+    if dtype == torch.float32:
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
+    else:
+        # same fp16 rounding points; the attention kernel sees other strides, nothing else differs
+        assert float((got.float() - ref.float()).norm() / ref.float().norm()) < 2e-3
+    assert got.shape == ref.shape
+
+
+def test_stack_of_one_layer_and_empty_stack():
+    m = _tiny(torch.float32, layers=1)
+    ids = torch.randint(0, 199, (1, 16), generator=torch.Generator().manual_seed(2))
+    with torch.no_grad():
+        h, kw = evalloop.layer_inputs(m, evalloop.LLAMA, ids)
+        ref = evalloop._call_layer(m.model.layers[0], h, kw)
+        got = fused.llama_stack([m.model.layers[0]], h.clone(), kw, ops=TorchGlue())
+        assert torch.allclose(got, ref, rtol=1e-5, atol=1e-5)
+        assert torch.equal(fused.llama_stack([], h.clone(), kw, ops=TorchGlue()), h)
+
+
+def test_torch_glue_matches_the_hf_modules_bit_for_bit():
+    from transformers.models.llama import modeling_llama as M
+    g = torch.Generator().manual_seed(3)
+    ops = TorchGlue()
+    for dtype in (torch.float16, torch.float32):
+        x = torch.randn(1, 8, 64, generator=g).to(dtype)
+        r = torch.randn(1, 8, 64, generator=g).to(dtype)
+        norm = M.LlamaRMSNorm(64, eps=1e-5).to(dtype)
+        norm.weight.data = torch.randn(64, generator=g).to(dtype)
+        s, y = ops.rmsnorm(x, norm.weight, norm.variance_epsilon, residual=r)
+        assert torch.equal(s, r + x) and torch.equal(y, norm(r + x))
+        assert torch.equal(ops.rmsnorm(x, norm.weight, norm.variance_epsilon), norm(x))
+        # rotary: token-major storage in place vs HF on (1, heads, S, hd)
+        S, nq, nkv, hd = 8, 4, 2, 16
+        q = torch.randn(1, S, nq * hd, generator=g).to(dtype)
+        k = torch.randn(1, S, nkv * hd, generator=g).to(dtype)
+        ang = torch.rand(S, hd // 2, generator=g) * 6
+        cos, sin = torch.cat((ang.cos(), ang.cos()), -1).to(dtype), torch.cat((ang.sin(), ang.sin()), -1).to(dtype)
+        qe, ke = M.apply_rotary_pos_emb(q.view(1, S, nq, hd).transpose(1, 2), k.view(1, S, nkv, hd).transpose(1, 2),
+                                        cos[None], sin[None])
+        q2, k2 = q.clone(), k.clone()
+        ops.rope_(q2, k2, cos, sin, hd)
+        assert torch.equal(q2.view(1, S, nq, hd).transpose(1, 2), qe) and torch.equal(k2.view(1, S, nkv, hd).transpose(1, 2), ke)
+        gate, up = torch.randn(1, 8, 96, generator=g).to(dtype), torch.randn(1, 8, 96, generator=g).to(dtype)
+        assert torch.equal(ops.silu_mul(gate, up), torch.nn.functional.silu(gate) * up)
+
+
+def test_supports_and_gate(monkeypatch):
+    m = _tiny(torch.float16)
+    ids = torch.randint(0, 199, (1, 32), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        h, kw = evalloop.layer_inputs(m, evalloop.LLAMA, ids)
+    assert fused.supports(m, h, kw)
+    assert not fused.supports(m, h.float(), kw)
+    assert not fused.supports(m, torch.cat((h, h)), kw)
+    monkeypatch.delenv('QUIP_FUSED_LAYER', raising=False)
+    assert not fused.enabled()
+    monkeypatch.setenv('QUIP_FUSED_LAYER', '1')
+    assert fused.enabled()
+
+
+def test_cuda_glue_refuses_cpu_tensors():
+    x = torch.zeros(1, 4, 64, dtype=torch.float16)
+    with pytest.raises(RuntimeError, match='CUDA device only'):
+        fused.CudaGlue().rmsnorm(x, torch.ones(64, dtype=torch.float16), 1e-5)

@@ -37,6 +37,17 @@ def test_argument_errors_surface_as_messages():
     assert b'multiple of 128' in lib.quip_last_error()
     with pytest.raises(_lib.QuipError):
         _lib.check(rc)
+    # glue entry points: shape / alignment / null checks come before any launch
+    assert lib.quip_rmsnorm(64, None, 64, None, 64, 4, 12, 1e-5, None) == 1 and b'multiple of 8' in lib.quip_last_error()
+    assert lib.quip_rmsnorm(64, None, 64, 64, 64, 4, 16, 1e-5, None) == 1 and b'without a residual' in lib.quip_last_error()
+    assert lib.quip_rmsnorm(64, None, 68, None, 64, 4, 16, 1e-5, None) == 1 and b'aligned' in lib.quip_last_error()
+    assert lib.quip_rmsnorm(None, None, 64, None, 64, 4, 16, 1e-5, None) == 1 and b'null' in lib.quip_last_error()
+    assert lib.quip_rmsnorm(64, None, 64, None, 64, 0, 16, 1e-5, None) == 0          # no rows: nothing to launch
+    assert lib.quip_rope(64, 64, 64, 64, 4, 4, 4, 24, None) == 1 and b'multiple of 16' in lib.quip_last_error()
+    assert lib.quip_rope(64, None, 64, 64, 4, 4, 4, 16, None) == 1 and b'head counts' in lib.quip_last_error()
+    assert lib.quip_rope(64, None, 64, 64, 0, 4, 0, 16, None) == 0
+    assert lib.quip_silu_mul(64, 64, 64, 12, None) == 1 and b'multiple of 8' in lib.quip_last_error()
+    assert lib.quip_silu_mul(64, 64, 64, 0, None) == 0
 
 
 @pytest.mark.parametrize('bits', [2, 3, 4])

@@ -272,6 +272,51 @@ def main():
             for (N, K) in [(4096, 4096), (11008, 4096), (4096, 11008)]:
                 r = bench_layer(N, K, 2048, 2, 'blocked', peaks); r['side_fused'] = sf; res.append(r); print(r, flush=True)
         lib.quip_config(b'side_fused', 1)
+    if 'glue' in what:
+        # glue kernels of csrc/glue.cu against the torch launches they replace, Llama-2-7B sizes at 2048 tokens
+        import sys as _sys
+        _sys.path.insert(0, ROOT)
+        from oracle.glue import TorchGlue            # the torch ops the HF modules issue (timed as the thing replaced)
+        from quip_b200.fused import CudaGlue
+        S, d, inter, nh, hd = 2048, 4096, 11008, 32, 128
+        cg, tg = CudaGlue(), TorchGlue()
+        cp = 24                                       # rotate over > L2 of distinct buffers
+        xs = [torch.randn(1, S, d, device='cuda').half() for _ in range(cp)]
+        w = torch.randn(d, device='cuda').half()
+        gs = [torch.randn(1, S, inter, device='cuda').half() for _ in range(6)]
+        cos, sin = torch.randn(S, hd, device='cuda').half(), torch.randn(S, hd, device='cuda').half()
+        hbm = peaks['hbm_gbs']
+        cases = [
+            ('rmsnorm', 2 * S * d * 2, lambda o: (lambda i: o.rmsnorm(xs[i % cp], w, 1e-5))),
+            ('add_rmsnorm', 4 * S * d * 2, lambda o: (lambda i: o.rmsnorm(xs[i % cp], w, 1e-5, residual=xs[(i + 1) % cp]))),
+            ('rope', 4 * S * d * 2, lambda o: (lambda i: o.rope_(xs[i % cp], xs[(i + 7) % cp], cos, sin, hd))),
+            ('silu_mul', 3 * S * inter * 2, lambda o: (lambda i: o.silu_mul(gs[i % 6], gs[(i + 1) % 6]))),
+        ]
+        for name, nbytes, mk in cases:
+            t_c, t_t = timeit(mk(cg)), timeit(mk(tg))
+            r = dict(what='glue', op=name, us_kernel=t_c, us_torch_ops=t_t, bytes=nbytes, gbs=nbytes / t_c * 1e-3,
+                     hbm_frac=nbytes / t_c * 1e-3 / hbm)
+            res.append(r); print(r, flush=True)
+    if 'stack' in what:
+        # one 2048-token sample through 4 packed Llama-2-7B decoder layers: HF layers vs the fused stack, graph replay
+        from transformers import LlamaConfig
+        from quip_b200 import evalloop
+        from quip_b200.quant import group_siblings
+        from quip_b200.synth import LLAMA2_7B, build_synthetic_model
+        cfg = LlamaConfig(**{**LLAMA2_7B, 'num_hidden_layers': 4})
+        model = build_synthetic_model(cfg, torch.device('cuda:0'), bits=2, incoh='blocked', rescale=True, seed=0, seqlen=2048)
+        group_siblings(model)
+        ids = torch.randint(0, cfg.vocab_size, (1, 2048), device='cuda')
+        for flag in ('0', '1'):
+            os.environ['QUIP_FUSED_LAYER'] = flag
+            with torch.no_grad():
+                for _ in range(2):
+                    nll = evalloop.sample_nll(model, evalloop.LLAMA, ids)
+                step = evalloop.GraphedSampleNLL(model, evalloop.LLAMA, ids)
+                t = timeit(lambda i: step.graph.replay(), iters=10)
+            r = dict(what='stack', fused=int(flag), layers=4, us_per_step=t, us_per_layer=t / 4, nll=float(nll))
+            res.append(r); print(r, flush=True)
+        os.environ.pop('QUIP_FUSED_LAYER', None)
     if 'layer' in what:
         for (N, K) in shapes:
             for M in (1, 2048):
