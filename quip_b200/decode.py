@@ -25,7 +25,9 @@ def _rotate_half(x):
 
 
 class GraphDecoder:
-    def __init__(self, model, max_len=256, batch=1):
+    def __init__(self, model, max_len=256, batch=1, ops=None):
+        """ops: provider of the fused glue kernels (quip_b200.fused.CudaGlue; picked up automatically when
+        QUIP_FUSED_LAYER=1 on a CUDA device), None for the torch glue."""
         cfg = model.config
         assert cfg.model_type == 'llama', 'GraphDecoder covers the Llama family'
         self.model, self.max_len, self.batch = model, int(max_len), int(batch)
@@ -50,10 +52,17 @@ class GraphDecoder:
         self._arange = torch.arange(self.max_len, device=self.dev)
         self._pos_host = 0
         # q/k/v and gate/up read the same input: their chains of few-token kernels run on parallel branches
-        self._side = [torch.cuda.Stream(device=self.dev) for _ in range(2)]
+        self._side = [torch.cuda.Stream(device=self.dev) for _ in range(2)] if self.dev.type == 'cuda' else None
+        if ops is None and self.dev.type == 'cuda':
+            from . import fused
+            if fused.enabled() and getattr(cfg, 'hidden_act', 'silu') == 'silu' and self.hd % 16 == 0:
+                ops = fused.CudaGlue()
+        self.ops = ops
 
     def _parallel(self, x, mods):
         """[m(x) for m in mods] with every module after the first on its own stream (graph branches when capturing)."""
+        if self._side is None:
+            return [m(x) for m in mods]
         main = torch.cuda.current_stream(self.dev)
         outs = [None] * len(mods)
         for i, m in enumerate(mods[1:], 1):
@@ -72,8 +81,47 @@ class GraphDecoder:
         self.k_cache.zero_()
         self.v_cache.zero_()
 
+    # the same step with the glue of csrc/glue.cu: 4 launches per layer instead of ~30 (at one token every torch
+    # elementwise op is a launch-latency-bound graph node)
+    def _step_fused(self):
+        m, ops = self.model.model, self.ops
+        B, nh, nkv, hd = self.batch, self.nh, self.nkv, self.hd
+        pos = self.position
+        h = m.embed_tokens(self.tokens)[:, None, :].contiguous()                           # (B, 1, hidden)
+        cos = self.cos.index_select(0, pos).expand(B, hd).contiguous()                     # one row per sequence
+        sin = self.sin.index_select(0, pos).expand(B, hd).contiguous()
+        mask = (self._arange <= pos)[None, None, None, :]
+        pend = None
+        for li, layer in enumerate(self.layers):
+            a, mlp = layer.self_attn, layer.mlp
+            n1, n2 = layer.input_layernorm, layer.post_attention_layernorm
+            if pend is None:
+                x = ops.rmsnorm(h, n1.weight, n1.variance_epsilon)
+            else:
+                h, x = ops.rmsnorm(h, n1.weight, n1.variance_epsilon, residual=pend)
+            q, k, v = self._parallel(x, [a.q_proj, a.k_proj, a.v_proj])
+            ops.rope_(q, k, cos, sin, hd)
+            self.k_cache[li].index_copy_(2, pos, k.view(B, 1, nkv, hd).transpose(1, 2))
+            self.v_cache[li].index_copy_(2, pos, v.view(B, 1, nkv, hd).transpose(1, 2))
+            kk, vv = self.k_cache[li], self.v_cache[li]
+            if nkv != nh:
+                kk = kk.repeat_interleave(nh // nkv, dim=1)
+                vv = vv.repeat_interleave(nh // nkv, dim=1)
+            o = F.scaled_dot_product_attention(q.view(B, 1, nh, hd).transpose(1, 2), kk, vv, attn_mask=mask,
+                                               scale=1.0 / math.sqrt(hd))
+            o = o.transpose(1, 2).reshape(B, 1, nh * hd)
+            h, x = ops.rmsnorm(h, n2.weight, n2.variance_epsilon, residual=a.o_proj(o))
+            gate, up = self._parallel(x, [mlp.gate_proj, mlp.up_proj])
+            pend = mlp.down_proj(ops.silu_mul(gate, up))
+        fn = m.norm
+        _, h = ops.rmsnorm(h, fn.weight, fn.variance_epsilon, residual=pend)
+        self.logits = self.model.lm_head(h)[:, 0, :]
+        self.position.add_(1)
+
     # one decode step on the static buffers (what the graph records)
     def _step(self):
+        if self.ops is not None:
+            return self._step_fused()
         m = self.model.model
         B, nh, nkv, hd = self.batch, self.nh, self.nkv, self.hd
         pos = self.position

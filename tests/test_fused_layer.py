@@ -91,3 +91,25 @@ def test_cuda_glue_refuses_cpu_tensors():
     x = torch.zeros(1, 4, 64, dtype=torch.float16)
     with pytest.raises(RuntimeError, match='CUDA device only'):
         fused.CudaGlue().rmsnorm(x, torch.ones(64, dtype=torch.float16), 1e-5)
+
+
+@pytest.mark.parametrize('nkv,use_ops', [(4, False), (2, False), (4, True), (2, True)])
+def test_decoder_steps_equal_hf_decode_with_kv_cache_on_cpu(nkv, use_ops):
+    """GraphDecoder's restated decode step (torch glue, and the fused-glue variant with the torch restatement injected)
+    against the HF forward with a KV cache, eagerly on the CPU in fp32."""
+    from quip_b200.decode import GraphDecoder
+    m = _tiny(torch.float32, nkv)
+    ids = torch.randint(0, 199, (2, 9), generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        dec = GraphDecoder(m, max_len=16, batch=2, ops=TorchGlue() if use_ops else None)
+        dec.cos, dec.sin = dec.cos.float(), dec.sin.float()                 # the decoder keeps fp16 tables for the GPU path
+        with torch.no_grad():
+            cos, sin = m.model.rotary_emb(torch.zeros(1, 1, 128), torch.arange(16)[None, :])
+        dec.cos, dec.sin = cos[0].contiguous(), sin[0].contiguous()
+        dec.k_cache, dec.v_cache = dec.k_cache.float(), dec.v_cache.float()
+        past = None
+        for i in range(ids.shape[1]):
+            out = m(ids[:, i:i + 1], past_key_values=past, use_cache=True)
+            past = out.past_key_values
+            got = dec.step(ids[:, i])
+            assert torch.allclose(got, out.logits[:, -1], rtol=2e-4, atol=2e-4), i

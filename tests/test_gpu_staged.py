@@ -103,3 +103,22 @@ def test_fused_stack_matches_hf_layers_on_a_packed_model(kv_heads, monkeypatch):
         assert abs(nll1 - nll0) / abs(nll0) < 1e-3
         stepper = evalloop.GraphedSampleNLL(model, evalloop.LLAMA, ids)          # the fused stack inside a CUDA graph
         assert abs(float(stepper(ids)) - nll1) / abs(nll1) < 1e-5
+
+
+@pytest.mark.parametrize('kv_heads', [4, 2])
+def test_fused_decode_step_matches_the_torch_glue_step(kv_heads, monkeypatch):
+    from transformers import LlamaConfig
+    from quip_b200.decode import GraphDecoder
+    from quip_b200.synth import build_synthetic_model
+    cfg = LlamaConfig(hidden_size=256, intermediate_size=512, num_hidden_layers=2, num_attention_heads=4,
+                      num_key_value_heads=kv_heads, vocab_size=320, max_position_embeddings=128)
+    model = build_synthetic_model(cfg, torch.device('cuda:0'), bits=2, incoh='blocked', rescale=True, seed=5, seqlen=64)
+    ids = torch.randint(0, 320, (2, 12), generator=torch.Generator().manual_seed(3)).cuda()
+    monkeypatch.delenv('QUIP_FUSED_LAYER', raising=False)
+    plain = GraphDecoder(model, max_len=16, batch=2).capture()
+    monkeypatch.setenv('QUIP_FUSED_LAYER', '1')
+    fusedd = GraphDecoder(model, max_len=16, batch=2).capture()
+    assert plain.ops is None and fusedd.ops is not None
+    for i in range(ids.shape[1]):
+        a, b = plain.step(ids[:, i]).float(), fusedd.step(ids[:, i]).float()
+        assert float((a - b).norm() / a.norm()) < 2e-3, i
