@@ -37,6 +37,15 @@ def llama_eval(model, testenc, dev, **kw):
     return evalloop.eval_ppl(model, ARCH, testenc, dev, **kw)
 
 
+@torch.no_grad()
+def llama_sequential(model, dataloader, dev, args, **kw):
+    """Reference llama_sequential (llama.py:26-171) as it was meant to run -- opt.py's flow on the Llama layers (the
+    shipped one reads an inconsistent flag set and a module global); returns {name: LayerParts} with the
+    Llama module names (not the OPT prefix of llama.py:154-155)."""
+    from . import quantize
+    return quantize.sequential(model, ARCH, dataloader, dev, args, **kw)
+
+
 def llama_pack(model, parts_by_name):
     make_quant(model, parts_by_name)
     qlayers = find_layers(model, [QuantLinear])

@@ -2,9 +2,8 @@
 
 Kept names (reference opt.py): get_opt (:14-26), opt_eval (:193-299), opt_pack3 (:303-315) ->
 opt_pack, load_quant3 (:317-348) / load_quant (:350-381), opt_multigpu (:384-428), benchmark
-(:431-482).  The quantization driver opt_sequential (:29-190) stays the reference's own (it is the
-producer side, SURVEY section 8 "out of scope"); run it under quip_b200.capture.Capture and hand the
-captured layer parts to opt_pack.
+(:431-482), opt_sequential (:29-190) -> quip_b200.quantize.sequential (torch LDLQ producer; a reference run under
+quip_b200.capture.Capture hands the same LayerParts to opt_pack).
 """
 import math
 
@@ -46,6 +45,13 @@ def get_opt(model, dtype=torch.float16):
 @torch.no_grad()
 def opt_eval(model, testenc, dev, **kw):
     return evalloop.eval_ppl(model, ARCH, testenc, dev, **kw)
+
+
+@torch.no_grad()
+def opt_sequential(model, dataloader, dev, args, **kw):
+    """Reference opt_sequential (opt.py:29-190) with `args` passed explicitly; returns {name: LayerParts}."""
+    from . import quantize
+    return quantize.sequential(model, ARCH, dataloader, dev, args, **kw)
 
 
 def opt_pack(model, parts_by_name):

@@ -153,10 +153,11 @@ def ldlq_rg_round(w, H, nbits, greedy_passes=0, block=128):
 # ----------------------------------------------------------------------------------------------------------------
 @torch.no_grad()
 def quantize_linear(weight, H, bits=2, method='ldlq', greedy_passes=0, qfn='b', rescale=True, incoh='blocked',
-                    percdamp=0.01, bias=None, generator=None, return_dense=False):
+                    percdamp=0.01, bias=None, generator=None, return_dense=False, damp=True):
     """weight (N, K) fp16/fp32, H (K, K) float32 from HessianAccumulator -> LayerParts (codes, affine map, 1/s, U, V).
 
-    incoh: 'blocked' | 'kron' | 'noperm' | None (no projection).  With return_dense also the fake-quantised dense fp16 weight
+    method: 'ldlq' | 'ldlq_rg' | 'nearest' (near.py: plain rounding, H unused).  incoh: 'blocked' | 'kron' | 'noperm' |
+    None (no projection).  damp: the --pre_gptqH step (dead columns + percdamp on the diagonal).  With return_dense also the fake-quantised dense fp16 weight
     the reference would leave in the layer (method.py:195-214), e.g. to propagate activations to the next layer."""
     dev, wdtype = weight.device, weight.dtype
     N, K = weight.shape
@@ -179,13 +180,18 @@ def quantize_linear(weight, H, bits=2, method='ldlq', greedy_passes=0, qfn='b', 
         w32 = butterfly_apply(U, w.float())                 # U W
         w = butterfly_apply(V, w32.T.contiguous()).T.contiguous().to(wdtype)      # (U W) V^T
         H = butterfly_apply(V, butterfly_apply(V, H).T.contiguous()).T.contiguous()
-    dead = torch.diagonal(H) == 0                           # method.py:182-192
-    H[dead, dead] = 1
-    w[:, dead] = 0
-    H = H + percdamp * torch.mean(torch.diagonal(H)) * torch.eye(K, device=dev)
+    if damp:                                                # --pre_gptqH, method.py:182-192
+        dead = torch.diagonal(H) == 0
+        H[dead, dead] = 1
+        w[:, dead] = 0
+        H = H + percdamp * torch.mean(torch.diagonal(H)) * torch.eye(K, device=dev)
 
     maxq = float(2 ** bits - 1)
-    rnd = ldlq_round if method == 'ldlq' else ldlq_rg_round
+    method = {'ldlqRG': 'ldlq_rg'}.get(method, method)      # the reference's spelling
+    if method not in ('ldlq', 'ldlq_rg', 'nearest'):
+        raise NotImplementedError(f'rounding method {method!r} (ldlq, ldlq_rg and nearest are implemented)')
+    rnd = {'ldlq': ldlq_round, 'ldlq_rg': ldlq_rg_round,
+           'nearest': lambda t, H_, nbits, passes: torch.clamp(torch.round(t), 0, 2 ** nbits - 1)}[method]
     if qfn == 'a':                                          # per-row asymmetric grid (quant.py:57-127)
         x = w.flatten(1)
         zero_ = torch.zeros(N, device=dev)
@@ -233,7 +239,7 @@ def proxy_loss(w_hat, w, H):
 # ----------------------------------------------------------------------------------------------------------------
 @torch.no_grad()
 def quantize_model(model, arch, calib_batches, dev=None, bits=2, method='ldlq', greedy_passes=0, qfn='b', rescale=True,
-                   incoh='blocked', percdamp=0.01, generator=None, pack=True, verbose=False):
+                   incoh='blocked', percdamp=0.01, generator=None, pack=True, verbose=False, damp=True):
     """Quantise every Linear inside the decoder layers of an OPT / Llama model, one decoder layer at a time, with the
     calibration activations produced by the already-quantised layers before it -- the flow of the reference's
     opt_sequential / llama_sequential (opt.py:29-190): per layer, (1) run the calibration samples through the layer with
@@ -267,7 +273,7 @@ def quantize_model(model, arch, calib_batches, dev=None, bits=2, method='ldlq', 
             parts, w_hat = quantize_linear(m.weight.data, accs[n].result(), bits=bits, method=method,
                                            greedy_passes=greedy_passes, qfn=qfn, rescale=rescale, incoh=incoh,
                                            percdamp=percdamp, bias=None if m.bias is None else m.bias.data,
-                                           generator=generator, return_dense=True)
+                                           generator=generator, return_dense=True, damp=damp)
             if verbose:
                 print(f'{prefix}.{li}.{n}: proxy loss {proxy_loss(w_hat.float(), m.weight.data.float(), accs[n].result()):.4f}')
             m.weight.data = w_hat.to(m.weight.data.dtype)
@@ -286,3 +292,36 @@ def _layers_prefix(model, layers):
         if mod is layers:
             return name
     raise ValueError('decoder layers are not a submodule of the model')
+
+
+_METHODS = {'ldlq': 'ldlq', 'ldlqRG': 'ldlq_rg', 'nearest': 'nearest'}
+_PROJ = {0: 'blocked', 1: 'kron', 2: 'noperm'}
+
+
+def options_from_args(args):
+    """The reference's command-line namespace (opt.py:484-600) -> quantize_model keywords.  `--incoh_processing` expands as
+    the reference does at opt.py:591-597 -- including its slip of setting `proj_extra` (unused) instead of
+    `pre_proj_extra`, so the projection stays the blocked one."""
+    g = lambda k, d=None: getattr(args, k, d)            # noqa: E731
+    quant = g('quant', 'nearest')
+    if quant not in _METHODS:
+        raise NotImplementedError(f'--quant {quant}: ldlq, ldlqRG and nearest are implemented')
+    if g('unbiased', False) or g('groupsize', -1) != -1 or g('lazy_batch', False):
+        raise NotImplementedError('--unbiased / --groupsize / --lazy_batch are not implemented')
+    pre_gptqH, pre_rescale, pre_proj, qfn = g('pre_gptqH', False), g('pre_rescale', False), g('pre_proj', False), g('qfn', 'a')
+    if g('incoh_processing', False):
+        pre_gptqH = pre_rescale = pre_proj = True
+        qfn = 'b'
+    if quant == 'nearest':
+        pre_gptqH = False                                 # Nearest has no preproc call (near.py:8-22)
+    return dict(bits=g('wbits'), method=_METHODS[quant], greedy_passes=g('npasses', 0), qfn=qfn, rescale=bool(pre_rescale),
+                incoh=_PROJ[g('pre_proj_extra', 0)] if pre_proj else None, percdamp=g('percdamp', 0.01), damp=bool(pre_gptqH))
+
+
+def sequential(model, arch, dataloader, dev, args, pack=False, generator=None, verbose=False):
+    """`opt_sequential(model, dataloader, dev)` / `llama_sequential` with the reference's flags (opt.py:29-190): dataloader is
+    the list of (input_ids, target) pairs datautils.get_loaders returns; `args` the namespace (the reference reads a module
+    global).  Returns {module name: LayerParts} -- the role of the reference's `quantizers` dict."""
+    batches = [b[0] if isinstance(b, (tuple, list)) else b for b in dataloader]
+    return quantize_model(model, arch, batches, dev=dev, pack=pack, generator=generator, verbose=verbose,
+                          **options_from_args(args))

@@ -131,3 +131,63 @@ def test_quantize_model_walks_the_decoder_stack():
         with torch.no_grad():
             errs[bits] = float((m(ids[0]).logits - base).norm() / base.norm())
     assert errs[4] < errs[2] and errs[4] < 0.2, errs
+
+
+def test_reference_flags_map_to_quantiser_options():
+    from types import SimpleNamespace as NS
+    o = qz.options_from_args(NS(quant='ldlqRG', wbits=2, npasses=2, incoh_processing=True, percdamp=0.01, qfn='a'))
+    assert o == dict(bits=2, method='ldlq_rg', greedy_passes=2, qfn='b', rescale=True, incoh='blocked', percdamp=0.01, damp=True)
+    o = qz.options_from_args(NS(quant='ldlq', wbits=4, npasses=0, pre_proj=True, pre_proj_extra=1, pre_gptqH=True, qfn='a'))
+    assert o['incoh'] == 'kron' and not o['rescale'] and o['qfn'] == 'a' and o['damp']
+    o = qz.options_from_args(NS(quant='nearest', wbits=3))
+    assert o['method'] == 'nearest' and o['incoh'] is None and not o['damp']
+    for bad in (NS(quant='gptq', wbits=4), NS(quant='ldlq', wbits=4, unbiased=True), NS(quant='allbal', wbits=2)):
+        with pytest.raises(NotImplementedError):
+            qz.options_from_args(bad)
+
+
+def test_nearest_is_plain_rounding_and_ldlq_beats_it():
+    g = torch.Generator().manual_seed(9)
+    W0 = (torch.randn(32, 128, generator=g) * 0.05).half()
+    acc = qz.HessianAccumulator(128)
+    acc.add_batch((torch.randn(1, 400, 128, generator=g) * (1 + 3 * torch.rand(128, generator=g))).half())
+    H = acc.result()
+    near, wn = qz.quantize_linear(W0, H, bits=3, method='nearest', qfn='a', rescale=False, incoh=None, damp=False, return_dense=True)
+    x = W0.float()
+    lo, hi = torch.minimum(x.min(1)[0], torch.zeros(32)), torch.maximum(x.max(1)[0], torch.zeros(32))
+    scale = ((hi - lo) / 7).reshape(-1, 1)
+    zero = torch.round(-lo.reshape(-1, 1) / scale)
+    assert torch.equal(near.codes, torch.clamp(torch.round(x / scale) + zero, 0, 7).to(torch.uint8))   # quant.py:6-9
+    ldl, wl = qz.quantize_linear(W0, H, bits=3, method='ldlq', qfn='a', rescale=False, incoh=None, return_dense=True)
+    assert qz.proxy_loss(wl.float(), W0.float(), H) < qz.proxy_loss(wn.float(), W0.float(), H)
+
+
+def test_opt_sequential_pack_save_and_reload_round_trip(tmp_path):
+    """Flags -> opt_sequential -> opt_pack -> state_dict -> load_quant: the packed checkpoint carries everything."""
+    from types import SimpleNamespace as NS
+    from transformers import OPTConfig, OPTForCausalLM
+    from quip_b200 import opt as O
+    from quip_b200.quant import QuantLinear
+    cfg = OPTConfig(hidden_size=128, ffn_dim=256, num_hidden_layers=1, num_attention_heads=4, vocab_size=256,
+                    max_position_embeddings=64, word_embed_proj_dim=128)
+    torch.manual_seed(0)
+    m = OPTForCausalLM(cfg).float().eval()
+    m.seqlen = 32
+    loader = [(torch.randint(0, 256, (1, 32), generator=torch.Generator().manual_seed(i)), None) for i in range(4)]
+    args = NS(quant='ldlq', wbits=2, npasses=0, incoh_processing=True, percdamp=0.01)
+    parts = O.opt_sequential(m, loader, 'cpu', args, generator=torch.Generator().manual_seed(2))
+    assert set(parts) == {f'model.decoder.layers.0.{n}' for n in
+                          ('self_attn.q_proj', 'self_attn.k_proj', 'self_attn.v_proj', 'self_attn.out_proj', 'fc1', 'fc2')}
+    O.opt_pack(m.half(), parts)
+    sd = m.state_dict()
+    path = tmp_path / 'packed.pt'
+    torch.save(sd, path)
+    m2 = O.load_quant(cfg, str(path))
+    q1 = {n: mod for n, mod in m.named_modules() if isinstance(mod, QuantLinear)}
+    q2 = {n: mod for n, mod in m2.named_modules() if isinstance(mod, QuantLinear)}
+    assert set(q1) == set(q2) == set(parts)
+    for n in q1:
+        assert q2[n].bits == 2 and q2[n].incoh == 'blocked' and q2[n].rescale
+        assert torch.equal(q1[n].qweight, q2[n].qweight)
+    sd2 = m2.state_dict()
+    assert set(sd) == set(sd2) and all(torch.equal(sd[k], sd2[k]) for k in sd)
