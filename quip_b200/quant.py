@@ -244,15 +244,24 @@ def convert_ref_qweight(ref_qweight: torch.Tensor, K: int, N: int, bits: int) ->
 # workspace (one per device, grown on demand; the 16 KiB header stays zero between calls)
 # ----------------------------------------------------------------------------------------------
 _workspaces = {}
+_retired = []          # outgrown workspaces: a captured CUDA graph may still address them, so they are never freed
 
 
 def _workspace(device, nbytes, stream_ptr=None):
-    """One workspace per (device, stream): kernels of different streams may run concurrently."""
+    """One workspace per (device, stream): kernels of different streams may run concurrently.
+
+    A workspace that is outgrown is kept alive (`_retired`) instead of freed: its address may be baked into a captured
+    CUDA graph (GraphDecoder, GraphedSampleNLL), and torch hands out stream handles from a small pool, so a later,
+    larger request can arrive under the same (device, stream) key.  Growth at least doubles, which bounds the retired
+    bytes by the size of the live workspace."""
     if stream_ptr is None:
         stream_ptr = torch.cuda.current_stream(device).cuda_stream
     key = (device, stream_ptr)
     ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _retired.append(ws)
+            nbytes = max(nbytes, 2 * ws.numel())
         ws = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
         _workspaces[key] = ws
     return ws

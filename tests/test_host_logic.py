@@ -230,3 +230,15 @@ def test_clock_sampler_summarises_only_rows_inside_the_timed_region():
     assert s['samples'] == 2 and s['sm_mhz'] == 1965.0 and s['sm_max_mhz'] == 1965.0 and s['reasons'] == ['sw_power_cap']
     clk.t0, clk.t1 = 20.0, 21.0                       # nothing landed inside: fall back to the last rows, never crash
     assert clk.summary()['samples'] == 2
+
+
+def test_outgrown_workspaces_stay_alive_for_captured_graphs():
+    from quip_b200 import quant as Q
+    dev = torch.device('cpu')
+    a = Q._workspace(dev, 1000, stream_ptr=12345)
+    assert a.numel() == 1 << 20 and Q._workspace(dev, 4096, stream_ptr=12345) is a          # reuse while it fits
+    ptr = a.data_ptr()
+    b = Q._workspace(dev, (1 << 20) + 1, stream_ptr=12345)
+    assert b.numel() == 2 << 20 and b is not a
+    assert any(t is a for t in Q._retired) and a.data_ptr() == ptr                           # the old block is not freed
+    assert Q._workspace(dev, 10, stream_ptr=777) is not b                                    # per-stream workspaces
