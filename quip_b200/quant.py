@@ -453,6 +453,10 @@ class QuantLinear(nn.Module):
         self._desc = None
         return super()._apply(fn, *a, **kw)
 
+    def _load_from_state_dict(self, *a, **kw):
+        self._desc = None                       # cached host copies (meta, fragment-order factors, inverse index) are stale
+        return super()._load_from_state_dict(*a, **kw)
+
     def _side(self, side, n):
         s = _lib.QuipSide()
         if not self.incoh:
