@@ -191,3 +191,44 @@ def test_opt_sequential_pack_save_and_reload_round_trip(tmp_path):
         assert torch.equal(q1[n].qweight, q2[n].qweight)
     sd2 = m2.state_dict()
     assert set(sd) == set(sd2) and all(torch.equal(sd[k], sd2[k]) for k in sd)
+
+
+# ---- the product quantiser against the LIVE REFERENCE's outputs (tests/golden, written by oracle/gen_golden_*.py) ----
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def test_product_rounding_reproduces_reference_codes():
+    """quip_b200.quantize.ldlq_round / ldlq_rg_round on the (w, H) of tests/golden/ldlq.npz: with one block (the
+    reference's column order of additions) the codes are the reference's bit for bit; 32-column blocks regroup fp32 sums
+    and may flip a near-tie."""
+    z = np.load(os.path.join(GOLDEN_DIR, 'ldlq.npz'))
+    for case in z['cases']:
+        key, nbits, npasses = str(case).split(':')
+        ci, meth = key.split('_')
+        w, H = torch.from_numpy(z[f'{ci}_w']), torch.from_numpy(z[f'{ci}_H'])
+        fn = qz.ldlq_round if meth == 'ldlq' else qz.ldlq_rg_round
+        want = z[f'{key}_out']
+        got = fn(w, H, int(nbits), int(npasses), block=w.shape[1]).numpy()
+        np.testing.assert_array_equal(got, want, err_msg=str(case))
+        blocked = fn(w, H, int(nbits), int(npasses), block=32).numpy()
+        assert np.mean(blocked == want) > 0.995, case
+
+
+@pytest.mark.parametrize('name', ['plain_a', 'rescale_a'])
+def test_product_quantize_linear_reproduces_reference_layers(name):
+    """Raw fp16 weight + calibration activations -> codes, per-row grid, 1/s: the reference's own quantised layer
+    (Balance.preproc -> fasterquant, captured in tests/golden/quantflow_*.npz)."""
+    z = np.load(os.path.join(GOLDEN_DIR, f'quantflow_{name}.npz'))
+    W0, X = torch.from_numpy(z['W0']), torch.from_numpy(z['X'])
+    acc = qz.HessianAccumulator(W0.shape[1])
+    acc.add_batch(X.unsqueeze(0))
+    method = {'ldlqRG': 'ldlq_rg'}.get(str(z['method']), str(z['method']))
+    parts = qz.quantize_linear(W0, acc.result(), bits=int(z['bits']), method=method, greedy_passes=int(z['npasses']),
+                               qfn=str(z['qfn']), rescale=bool(int(z['rescale'])), incoh=None)
+    assert np.mean(parts.codes.numpy() == z['codes']) > 0.995
+    assert np.mean(parts.grid.numpy().view(np.uint16) == z['grid'].view(np.uint16)) > 0.995
+    if int(z['rescale']):
+        np.testing.assert_allclose(parts.scaleWH.numpy(), z['scaleWH'], rtol=1e-5)
+    # per-row grid: W = scales * code - zeros with scales = scale, zeros = zero * scale (quant.py:186-191)
+    np.testing.assert_allclose(parts.scales.numpy().ravel(), z['scale'].ravel(), rtol=1e-6)
+    np.testing.assert_allclose(parts.zeros.numpy().ravel(), (z['zero'] * z['scale']).ravel(), rtol=1e-6)
