@@ -232,3 +232,24 @@ def test_product_quantize_linear_reproduces_reference_layers(name):
     # per-row grid: W = scales * code - zeros with scales = scale, zeros = zero * scale (quant.py:186-191)
     np.testing.assert_allclose(parts.scales.numpy().ravel(), z['scale'].ravel(), rtol=1e-6)
     np.testing.assert_allclose(parts.zeros.numpy().ravel(), (z['zero'] * z['scale']).ravel(), rtol=1e-6)
+
+
+def test_optq_equals_ldlq_on_a_fake_layer():
+    """The reference's one self-check (optq_ldlq_equiv.py, which needs CUDA and only prints the agreement): OPTQ, restated
+    in oracle/optq.py, and the product's LDLQ pick the same grid points -- LDLQ walks columns last to first, OPTQ first to
+    last, so LDLQ runs on the column-reversed problem.  Both must beat nearest rounding on the proxy loss."""
+    from oracle import optq
+    bits = 3
+    w, H = optq.fake_layer(192, 160, seed=1)
+    codes_optq, scale, zero = optq.optq_codes(w, H, bits)
+    t = torch.clamp(w / scale + zero, 0, 2 ** bits - 1)                  # the weight in grid units
+    rev = torch.arange(w.shape[1] - 1, -1, -1)
+    codes_ldlq = qz.ldlq_round(t[:, rev].float(), H[rev][:, rev].float(), bits, 0, block=64).double()[:, rev]
+    # fp32 feedback sums and the tie rule (floor(v + 0.5) vs round-half-even) flip a near-tie now and then; the flip then
+    # propagates along its row
+    assert float((codes_ldlq == codes_optq).double().mean()) > 0.995
+    deq = lambda c: scale * (c - zero)                                    # noqa: E731
+    nearest = torch.clamp(torch.round(t), 0, 2 ** bits - 1)
+    loss = lambda q: float(torch.trace((q - w) @ H @ (q - w).T))         # noqa: E731
+    assert loss(deq(codes_ldlq)) < 0.7 * loss(deq(nearest)) and loss(deq(codes_optq)) < 0.7 * loss(deq(nearest))
+    assert abs(loss(deq(codes_ldlq)) / loss(deq(codes_optq)) - 1) < 0.01
