@@ -242,3 +242,49 @@ def test_outgrown_workspaces_stay_alive_for_captured_graphs():
     assert b.numel() == 2 << 20 and b is not a
     assert any(t is a for t in Q._retired) and a.data_ptr() == ptr                           # the old block is not freed
     assert Q._workspace(dev, 10, stream_ptr=777) is not b                                    # per-stream workspaces
+
+
+# ---- property tests (hypothesis): pack <-> unpack for 2/3/4 bits, the reference layouts included ----
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=25, deadline=None)
+@given(bits=st.sampled_from([2, 3, 4]), nb=st.integers(1, 4), kb=st.integers(1, 3), seed=st.integers(0, 2 ** 31 - 1),
+       fill=st.sampled_from(['random', 'zeros', 'max', 'ramp']))
+def test_pack_unpack_round_trip_property(bits, nb, kb, seed, fill):
+    N, K = 16 * nb, 128 * kb
+    top = (1 << bits) - 1
+    if fill == 'random':
+        codes = np.random.default_rng(seed).integers(0, top + 1, size=(N, K), dtype=np.uint8)
+    elif fill == 'zeros':
+        codes = np.zeros((N, K), np.uint8)
+    elif fill == 'max':
+        codes = np.full((N, K), top, np.uint8)
+    else:
+        codes = ((np.arange(N)[:, None] * 7 + np.arange(K)[None, :]) % (top + 1)).astype(np.uint8)
+    q = Q.pack_codes(torch.from_numpy(codes), bits)
+    assert q.dtype == torch.int32 and q.numel() == Q.packed_words(N, K, bits) == N * K * bits // 32
+    np.testing.assert_array_equal(q.numpy(), opk.native_pack(codes, bits))                 # the oracle's layout, word for word
+    np.testing.assert_array_equal(Q.unpack_codes(q, N, K, bits).numpy(), codes)
+    np.testing.assert_array_equal(opk.native_unpack(q.numpy(), N, K, bits), codes)
+    # every code lands in exactly `bits` bits: flipping one code changes one word (two when a 3-bit code straddles)
+    c2 = codes.copy()
+    c2[seed % N, seed % K] ^= 1
+    changed = int((Q.pack_codes(torch.from_numpy(c2), bits) != q).sum())
+    assert 1 <= changed <= 2
+
+
+@settings(max_examples=15, deadline=None)
+@given(bits=st.sampled_from([2, 3, 4]), nb=st.integers(1, 3), seed=st.integers(0, 2 ** 31 - 1))
+def test_reference_layout_round_trip_property(bits, nb, seed):
+    """The reference's own layouts, (K*bits/32, N) int32 (quant.py:192-220, zeroShot/models/quant.py:193-199), as restated
+    in oracle/packing.py (pinned to the reference's words in test_oracle_golden.py): pack <-> unpack is the identity and the
+    word count is what Quant3Linear / Quant4Linear register.  (quip_convert_ref, the GPU converter, is checked against the
+    same functions in tests/test_gpu_kernels.py.)"""
+    N, K = 16 * nb, 128
+    codes = np.random.default_rng(seed).integers(0, 1 << bits, size=(N, K), dtype=np.uint8)
+    pack, unpack = {2: (opk.ref_pack2, opk.ref_unpack2), 3: (opk.ref_pack3, opk.ref_unpack3),
+                    4: (opk.ref_pack4, opk.ref_unpack4)}[bits]
+    words = pack(codes)
+    assert words.shape == (K * bits // 32, N) and words.dtype == np.int32
+    np.testing.assert_array_equal(unpack(words, K), codes)
