@@ -400,9 +400,12 @@ def main():
             gsec, _ = graph_decode_benchmark(model, ids_dev[0][:, :48], max_len=64)
             from quip_b200.decode import graph_decode_throughput
             sweep = {}
-            for bsz in (1, 2, 4, 8):
-                tps, step_ms = graph_decode_throughput(model, bsz, steps=24, max_len=32)
-                sweep[str(bsz)] = dict(tokens_per_s=tps, ms_per_step=step_ms)
+            for bsz in (1, 2, 4, 8, 16, 32):                    # BASELINE configs[4]: batch 1-32 sweep
+                try:
+                    tps, step_ms = graph_decode_throughput(model, bsz, steps=24, max_len=32)
+                    sweep[str(bsz)] = dict(tokens_per_s=tps, ms_per_step=step_ms)
+                except Exception as e:                          # keep the sizes that ran
+                    sweep[str(bsz)] = dict(error=repr(e)[:160])
             out['decode']['graph_decode_batch_sweep'] = sweep
             out['decode']['graph_decode'] = dict(tokens_per_s=1.0 / gsec, median_ms_per_token=gsec * 1e3, tokens=48,
                                                  note='quip_b200.decode.GraphDecoder: the same decode step (attention, norms, '
