@@ -38,6 +38,7 @@ int qgemm_ts(const QuipLinearDesc* d, const __half* x, const float* xsum, const 
              cudaStream_t s);
 
 extern int g_gather_rows, g_pass_min_tiles, g_fewtok;   // rot.cu
+extern int g_fewtok_max_m;                               // rot_fewtok.cu: token count up to which the few-token kernels run (8)
 bool side_fused_ok(const QuipSide* sd, int n);               // rot_side.cu
 int side_fused(const QuipSide* sd, const __half* in, __half* out, int64_t M, const int32_t* in_idx, const float* in_scale,
                const int32_t* out_idx, const __half* out_bias, float* xsum, cudaStream_t s);
@@ -192,6 +193,11 @@ extern "C" int quip_config(const char* key, int value) {
   if (!strcmp(key, "side_fused")) { g_side_fused = value; return QUIP_OK; }
   if (!strcmp(key, "pdl")) { g_pdl = value; return QUIP_OK; }
   if (!strcmp(key, "fewtok")) { g_fewtok = value; return QUIP_OK; }
+  if (!strcmp(key, "fewtok_max_m")) {
+    QUIP_CHECK_ARG(value >= 8 && value <= 32, "quip_config: fewtok_max_m must be in 8..32");
+    g_fewtok_max_m = value;
+    return QUIP_OK;
+  }
   if (!strcmp(key, "gemv")) { g_use_gemv = value; return QUIP_OK; }
   if (!strcmp(key, "gv_rbc")) { g_gv_rbc = value; return QUIP_OK; }
   if (!strcmp(key, "gv_stream")) { g_gv_stream = value; return QUIP_OK; }
@@ -279,7 +285,7 @@ extern "C" int quip_qlinear_forward(const QuipLinearDesc* d, const void* x_, voi
   const int vpass = d->V.n ? d->V.npass : 0;
   const bool need_xsum = !(d->flags & QUIP_FLAG_SYMMETRIC) && M > SKINNY_MAX_M;
   bool have_xsum = false;
-  if (g_side_fused && M > 8 && vpass == 2 && side_fused_ok(&d->V, K)) {
+  if (g_side_fused && M > g_fewtok_max_m && vpass == 2 && side_fused_ok(&d->V, K)) {
     // many tokens: the whole side in one kernel, 16 token rows resident in shared memory
     if (int e = side_fused(&d->V, x, bufA, M, d->V.idx, d->inv_scale, nullptr, nullptr, need_xsum ? xsum : nullptr, s)) return e;
     cur = bufA;
@@ -287,7 +293,7 @@ extern "C" int quip_qlinear_forward(const QuipLinearDesc* d, const void* x_, voi
   } else {
     // few tokens: the gather (index + 1/s) rides on the first pass's operand load
     // (small blocks only: a 688-wide block is shared by 21 CTAs, which would each repeat the indexed reads)
-    const bool fuse_in = g_fewtok && M <= 8 && vpass > 0 && d->V.pass[0].p <= 128 && pass_fewtok_ok(&d->V.pass[0], M, K);
+    const bool fuse_in = g_fewtok && M <= g_fewtok_max_m && vpass > 0 && d->V.pass[0].p <= 128 && pass_fewtok_ok(&d->V.pass[0], M, K);
     if ((d->V.idx || d->inv_scale) && !fuse_in) {
       if (int e = quip_gather(cur, bufA, M, K, d->V.n ? d->V.idx : nullptr, d->inv_scale, nullptr, stream)) return e;
       cur = bufA;
@@ -313,13 +319,13 @@ extern "C" int quip_qlinear_forward(const QuipLinearDesc* d, const void* x_, voi
   if (!u_on) return QUIP_OK;
 
   // ---- N side: y = passes(z)[idx] + bias ----
-  if (g_side_fused && M > 8 && d->U.npass == 2 && side_fused_ok(&d->U, N))
+  if (g_side_fused && M > g_fewtok_max_m && d->U.npass == 2 && side_fused_ok(&d->U, N))
     return side_fused(&d->U, zbuf, y, M, nullptr, nullptr, d->U.idx, (const __half*)d->bias, nullptr, s);
   const __half* zc = zbuf;
   const int np = d->U.npass;
   bool tail_gather = d->U.idx || d->bias;
   // few tokens: the last pass scatters through the inverse index and adds the bias itself
-  const bool fuse_out = tail_gather && g_fewtok && M <= 8 && np > 0 && (!d->U.idx || d->U.inv_idx) &&
+  const bool fuse_out = tail_gather && g_fewtok && M <= g_fewtok_max_m && np > 0 && (!d->U.idx || d->U.inv_idx) &&
                         pass_fewtok_ok(&d->U.pass[np - 1], M, N);
   if (fuse_out) tail_gather = false;
   for (int i = 0; i < np; ++i) {

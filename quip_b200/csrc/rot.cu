@@ -398,6 +398,7 @@ static int launch_gather(const __half* in, __half* out, int64_t M, int n, const 
 }
 
 namespace quip {
+extern int g_fewtok_max_m;
 bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n);
 int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
                 const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s);
@@ -416,7 +417,7 @@ extern "C" int quip_gather(const void* in, void* out, int64_t M, int32_t n, cons
   const __half* i = (const __half*)in;
   __half* o = (__half*)out;
   const __half* b = (const __half*)bias;
-  if (g_fewtok && M <= 8) return gather_fewtok(i, o, M, n, idx, scale, b, s);
+  if (g_fewtok && M <= g_fewtok_max_m) return gather_fewtok(i, o, M, n, idx, scale, b, s);
   // rows per CTA: share the index vector across rows, but keep several waves of CTAs so that one CTA's load
   // phase overlaps another's permute phase
   const size_t row = (size_t)n * sizeof(__half);

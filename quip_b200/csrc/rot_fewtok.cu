@@ -27,13 +27,17 @@ constexpr int FT_XPT = 6;              // input elements staged per thread (cove
 //                       (the K-side gather + 1/s of quip_gather, rounded to fp16 exactly as it rounds)
 //   out_inv / out_bias: the pass writes out[m][out_inv[pos]] = value + out_bias[out_inv[pos]]
 //                       (the N-side gather y[j] = layout[idx[j]] + bias[j], out_inv = idx^-1)
+//
+// NG = groups of 8 tokens (the MMA's n): the factor fragments are loaded once and reused by every group, so 9..32
+// tokens (batched decode) cost a few more MMAs per task, not more factor traffic.
+template <int NG>
 __global__ void __launch_bounds__(FT_WARPS * 32)
 pass_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, const __half* __restrict__ F, int M, int n,
                    int p, int nblk, int strided, int shared, int kparts, int steps_per_part,
                    const int32_t* __restrict__ in_idx, const float* __restrict__ in_scale,
                    const int32_t* __restrict__ out_inv, const __half* __restrict__ out_bias, int nb_cta) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float red[FT_WARPS][16][9];
+  __shared__ float red[NG][FT_WARPS][16][9];
   __half* xs = reinterpret_cast<__half*>(smem_raw);        // [M][xld]: the input blocks this CTA multiplies
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int rtiles = p >> 4;                               // 16-row tiles per block
@@ -126,50 +130,70 @@ pass_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
   __syncthreads();
 
   // ---- tokens with the same k labelling; columns >= M re-read the last token ----
-  const __half* xrow = xs + min(g, M - 1) * xld + (b - b_first) * p;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const __half* xrow[NG];
+#pragma unroll
+  for (int q = 0; q < NG; ++q) xrow[q] = xs + min(8 * q + g, M - 1) * xld + (b - b_first) * p;
+  float acc[NG][4];
+#pragma unroll
+  for (int q = 0; q < NG; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[q][c] = 0.f;
 #pragma unroll
   for (int u = 0; u < FT_PAIRS; ++u) {
     if (u < npair) {
-      const uint4 v = *reinterpret_cast<const uint4*>(xrow + (s0 + 2 * u) * 16 + 8 * t);
-      const uint32_t b0[2] = {v.x, v.y}, b1[2] = {v.z, v.w};
       // a lane's four consecutive k are MMA slots (2t, 2t+1, 2t+8, 2t+9) on both operands
       const uint32_t a0[4] = {a_lo[u].x, a_hi[u].x, a_lo[u].y, a_hi[u].y};
       const uint32_t a1[4] = {a_lo[u].z, a_hi[u].z, a_lo[u].w, a_hi[u].w};
-      mma16816(acc, a0, b0);
-      mma16816(acc, a1, b1);
+#pragma unroll
+      for (int q = 0; q < NG; ++q) {
+        const uint4 v = *reinterpret_cast<const uint4*>(xrow[q] + (s0 + 2 * u) * 16 + 8 * t);
+        const uint32_t b0[2] = {v.x, v.y}, b1[2] = {v.z, v.w};
+        mma16816(acc[q], a0, b0);
+        mma16816(acc[q], a1, b1);
+      }
     }
   }
   if (tail) {
-    const uint2 v = *reinterpret_cast<const uint2*>(xrow + (s1 - 1) * 16 + 4 * t);
-    const uint32_t bfrag[2] = {v.x, v.y};
     const uint32_t a[4] = {t_lo.x, t_hi.x, t_lo.y, t_hi.y};
-    mma16816(acc, a, bfrag);
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+      const uint2 v = *reinterpret_cast<const uint2*>(xrow[q] + (s1 - 1) * 16 + 4 * t);
+      const uint32_t bfrag[2] = {v.x, v.y};
+      mma16816(acc[q], a, bfrag);
+    }
   }
 
-  // ---- sum the k parts in a fixed order, store rows g / g+8 for tokens 2t, 2t+1 ----
+  // ---- sum the k parts in a fixed order, store rows g / g+8 for tokens 8q + 2t, 8q + 2t + 1 ----
   if (kparts > 1) {
-    red[warp][g][2 * t] = acc[0]; red[warp][g][2 * t + 1] = acc[1];
-    red[warp][g + 8][2 * t] = acc[2]; red[warp][g + 8][2 * t + 1] = acc[3];
+#pragma unroll
+    for (int q = 0; q < NG; ++q) {
+      red[q][warp][g][2 * t] = acc[q][0]; red[q][warp][g][2 * t + 1] = acc[q][1];
+      red[q][warp][g + 8][2 * t] = acc[q][2]; red[q][warp][g + 8][2 * t + 1] = acc[q][3];
+    }
     __syncthreads();
     if (part != 0) return;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) acc[c] = 0.f;
-    for (int q = 0; q < kparts; ++q) {
-      acc[0] += red[warp + q][g][2 * t]; acc[1] += red[warp + q][g][2 * t + 1];
-      acc[2] += red[warp + q][g + 8][2 * t]; acc[3] += red[warp + q][g + 8][2 * t + 1];
+    for (int q = 0; q < NG; ++q) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[q][c] = 0.f;
+      for (int w = 0; w < kparts; ++w) {
+        acc[q][0] += red[q][warp + w][g][2 * t]; acc[q][1] += red[q][warp + w][g][2 * t + 1];
+        acc[q][2] += red[q][warp + w][g + 8][2 * t]; acc[q][3] += red[q][warp + w][g + 8][2 * t + 1];
+      }
     }
   }
   if (!live) return;
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int tok = 2 * t + (c & 1), h = c >> 1;
-    if (tok < M) {
-      // fused bias: the pass result is rounded to fp16 first, as the stand-alone gather would read it
-      const float v = out_bias ? __half2float(__float2half_rn(acc[c])) + dbias[h] : acc[c];
-      out[(int64_t)tok * n + dst[h]] = __float2half_rn(v);
+  for (int q = 0; q < NG; ++q)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int tok = 8 * q + 2 * t + (c & 1), h = c >> 1;
+      if (tok < M) {
+        // fused bias: the pass result is rounded to fp16 first, as the stand-alone gather would read it
+        const float v = out_bias ? __half2float(__float2half_rn(acc[q][c])) + dbias[h] : acc[q][c];
+        out[(int64_t)tok * n + dst[h]] = __float2half_rn(v);
+      }
     }
-  }
 }
 
 // out[m][l] = in[m][idx ? idx[l] : l] * (scale ? scale[src] : 1) + (bias ? bias[l] : 0), one thread per 8 outputs
@@ -207,8 +231,10 @@ gather_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, in
 
 int launch_pdl(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args);   // api.cu
 
+int g_fewtok_max_m = 8;       // quip_config("fewtok_max_m", 32): batched decode (9..32 tokens) through the few-token kernels
+
 bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n) {
-  return M <= 8 && ps->p % 16 == 0 && ps->p >= 16 && (n % 8 == 0) && (((uintptr_t)ps->factors) & 15) == 0;
+  return M <= g_fewtok_max_m && M <= 32 && ps->p % 16 == 0 && ps->p >= 16 && (n % 8 == 0) && (((uintptr_t)ps->factors) & 15) == 0;
 }
 
 int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
@@ -231,7 +257,20 @@ int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, in
   void* args[] = {(void*)&in, (void*)&out, (void*)&F, (void*)&Mi, (void*)&n, (void*)&p, (void*)&nblk,
                   (void*)&strided, (void*)&shared, (void*)&kparts, (void*)&steps_per_part, (void*)&in_idx,
                   (void*)&in_scale, (void*)&out_inv, (void*)&out_bias, (void*)&nb_cta};
-  if (int e = launch_pdl((const void*)pass_fewtok_kernel, dim3((unsigned)ceil_div(groups, per_cta)), dim3(FT_WARPS * 32), smem, s, args))
+  const void* kern = M <= 8 ? (const void*)pass_fewtok_kernel<1>
+                            : (M <= 16 ? (const void*)pass_fewtok_kernel<2> : (const void*)pass_fewtok_kernel<4>);
+  if (smem > 48 * 1024) {                                  // many tokens x two 688-wide blocks: opt in once per device
+    QUIP_CHECK_ARG(smem <= 200 * 1024, "few-token pass: %zu bytes of token staging", smem);
+    static bool attr_done[64][3] = {};
+    int dev = 0;
+    QUIP_CUDA(cudaGetDevice(&dev));
+    const int ki = M <= 8 ? 0 : (M <= 16 ? 1 : 2);
+    if (!attr_done[dev & 63][ki]) {
+      QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_done[dev & 63][ki] = true;
+    }
+  }
+  if (int e = launch_pdl(kern, dim3((unsigned)ceil_div(groups, per_cta)), dim3(FT_WARPS * 32), smem, s, args))
     return e;
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return QUIP_OK;

@@ -122,3 +122,36 @@ def test_fused_decode_step_matches_the_torch_glue_step(kv_heads, monkeypatch):
     for i in range(ids.shape[1]):
         a, b = plain.step(ids[:, i]).float(), fusedd.step(ids[:, i]).float()
         assert float((a - b).norm() / a.norm()) < 2e-3, i
+
+
+@pytest.mark.parametrize('K,N,bits,incoh', [(4096, 4096, 2, 'blocked'), (4096, 11008, 2, 'blocked'), (11008, 4096, 2, 'blocked'),
+                                             (8192, 1024, 2, 'blocked'), (768, 3072, 4, None), (4096, 4096, 3, 'kron'),
+                                             (2048, 8192, 4, 'noperm')])
+def test_batched_decode_token_counts_through_the_few_token_passes(K, N, bits, incoh):
+    """quip_config('fewtok_max_m', 32): 9..32 tokens run the few-token passes (pass_fewtok_kernel<2>, <4>: the factor
+    fragments loaded once, two or four groups of 8 tokens) instead of the 16-token-tile side kernel.  Same results as the
+    default route up to the accumulation order, and within the layer tolerance of the fp32 torch restatement."""
+    from gpu_util import torch_reference_forward
+    from quip_b200 import _lib
+    from quip_b200 import quant as Q
+    from quip_b200.synth import synth_layer_parts
+    lib = _lib.load()
+    tp = synth_layer_parts(K=K, N=N, bits=bits, incoh=incoh, rescale=incoh is not None, bias=(N in (1024, 3072)),
+                           seed=K + N, qfn='a')
+    ql = Q.QuantLinear(infeatures=K, outfeatures=N, **Q.spec_from_parts(tp)).cuda()
+    ql.pack_parts(tp)
+    x = (torch.randn(32, K, device='cuda') * (1 + 3 * torch.rand(K, device='cuda'))).half()
+    want = torch_reference_forward(ql, x)
+    try:
+        for M in (8, 9, 15, 16, 17, 24, 31, 32):
+            _lib.check(lib.quip_config(b'fewtok_max_m', 8))
+            base = ql(x[:M]).float()
+            _lib.check(lib.quip_config(b'fewtok_max_m', 32))
+            y = ql(x[:M]).float()
+            assert float((y - want[:M]).norm() / want[:M].norm()) < 1.5e-3, (M, 'vs torch')
+            assert float((y - base).norm() / base.norm()) < 1e-3, (M, 'vs default route')
+            if M == 8:
+                assert torch.equal(y, base)                      # the limit does not touch the <= 8 token route
+    finally:
+        lib.quip_config(b'fewtok_max_m', 8)
+    assert lib.quip_config(b'fewtok_max_m', 33) != 0 and lib.quip_config(b'fewtok_max_m', 4) != 0

@@ -272,6 +272,16 @@ def main():
             for (N, K) in [(4096, 4096), (11008, 4096), (4096, 11008)]:
                 r = bench_layer(N, K, 2048, 2, 'blocked', peaks); r['side_fused'] = sf; res.append(r); print(r, flush=True)
         lib.quip_config(b'side_fused', 1)
+    if 'batchdecode' in what:
+        # 9..32 tokens through one QuantLinear: default route (16-token-tile side kernel) vs the few-token passes
+        lib = _lib.load()
+        for lim in (8, 32):
+            lib.quip_config(b'fewtok_max_m', lim)
+            for (N, K) in shapes:
+                for M in (8, 16, 32):
+                    r = bench_layer(N, K, M, 2, 'blocked', peaks, copies=4); r['fewtok_max_m'] = lim
+                    res.append(r); print(r, flush=True)
+        lib.quip_config(b'fewtok_max_m', 8)
     if 'glue' in what:
         # glue kernels of csrc/glue.cu against the torch launches they replace, Llama-2-7B sizes at 2048 tokens
         import sys as _sys

@@ -12,6 +12,8 @@ timeout 300 python tools/microbench.py --what glue --out $out/glue.json > $out/g
 echo "glue microbench exit $?" | tee -a $out/summary.txt
 timeout 420 python tools/microbench.py --what stack --out $out/stack.json > $out/stack.log 2>&1
 echo "stack microbench exit $?" | tee -a $out/summary.txt
+timeout 300 python tools/microbench.py --what batchdecode --out $out/batchdecode.json > $out/batchdecode.log 2>&1
+echo "batched-decode microbench exit $?" | tee -a $out/summary.txt
 QUIP_FUSED_LAYER=0 timeout 420 python bench.py --steps 8 --warmup 3 --no-decode --no-cpu-baseline > $out/bench_hf_glue.json 2> $out/bench_hf_glue.err
 QUIP_FUSED_LAYER=1 timeout 420 python bench.py --steps 8 --warmup 3 --no-cpu-baseline > $out/bench_fused_glue.json 2> $out/bench_fused_glue.err
 python - <<'PY' | tee -a gpurun_out/staged/summary.txt
