@@ -164,6 +164,75 @@ def decode_leg(model, dev, pk):
                 roofline_tokens_per_s=pk['hbm_gbs'] * 1e9 / nbytes)
 
 
+def pick_glue(model, prime):
+    """Which glue runs between the packed linears of a decoder layer in this run: the HF modules' own torch launches, or the
+    fused kernels of csrc/glue.cu (quip_b200/fused.py).  QUIP_FUSED_LAYER=0/1 forces one; otherwise both are run here on
+    the first two decoder layers of the benchmark model with one real sample, and the fused stack is used only if its
+    output agrees with the HF layers' (relative error < 1e-3, the layer tolerance) AND it is faster.  Returns a dict for
+    the JSON line; sets QUIP_FUSED_LAYER for the rest of the process."""
+    from quip_b200 import evalloop, fused
+    forced = os.environ.get('QUIP_FUSED_LAYER')
+    if forced is not None:
+        return dict(mode='fused' if forced == '1' else 'hf', chosen_by='QUIP_FUSED_LAYER=' + forced)
+    info = dict(mode='hf', chosen_by='in-run check')
+    try:
+        with torch.no_grad():
+            h, kw = evalloop.layer_inputs(model, evalloop.LLAMA, prime)
+            if not fused.supports(model, h, kw):
+                info['why'] = 'model not supported by the fused stack'
+                return info
+            layers = list(model.model.layers)[:2]
+
+            def hf():
+                r = h
+                for layer in layers:
+                    r = evalloop._call_layer(layer, r, kw)
+                return r
+
+            def fu():
+                return fused.llama_stack(layers, h.clone(), kw)
+
+            ref, got = hf().float(), fu().float()
+            err = float((got - ref).norm() / ref.norm())
+            times = {}
+            for name, fn in (('hf', hf), ('fused', fu)):
+                for _ in range(2):
+                    fn()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                times[name] = e0.elapsed_time(e1) / 3 / len(layers)
+            info.update(rel_err_vs_hf_layers=err, ms_per_layer_hf=times['hf'], ms_per_layer_fused=times['fused'],
+                        note='eager launches, first two decoder layers, one 2048-token sample')
+            if err < 1e-3 and times['fused'] < times['hf']:
+                info['mode'] = 'fused'
+    except Exception as e:                                  # any failure keeps the HF glue
+        info['why'] = repr(e)[:200]
+    os.environ['QUIP_FUSED_LAYER'] = '1' if info['mode'] == 'fused' else '0'
+    return info
+
+
+def decode_glue_ok(model, dev):
+    """The decode step with the fused glue (GraphDecoder._step_fused) against the torch-glue step on the same model: eight
+    tokens, two sequences, logits within 2e-3 (they differ by the summation order of the norms)."""
+    from quip_b200.decode import GraphDecoder
+    from quip_b200.fused import CudaGlue
+    ids = torch.randint(0, model.config.vocab_size, (8, 2), generator=torch.Generator().manual_seed(7)).to(dev)
+    with torch.no_grad():
+        os.environ['QUIP_FUSED_LAYER'] = '0'
+        plain = GraphDecoder(model, max_len=16, batch=2)
+        fusedd = GraphDecoder(model, max_len=16, batch=2, ops=CudaGlue())
+        worst = 0.0
+        for i in range(ids.shape[0]):
+            a, b = plain.step(ids[i]).float(), fusedd.step(ids[i]).float()
+            worst = max(worst, float((a - b).norm() / a.norm()))
+    return worst < 2e-3, worst
+
+
 def cpu_reference_arm(steps, warmup):
     """The reference's own implementation of the path on the host cores: dense fp16 decoder layer through
     the reference loop (oracle/evalloop.py).  Bounded sample: ONE decoder layer x ONE 2048-token sample per
@@ -263,6 +332,12 @@ def main():
         for _ in range(2):
             evalloop.sample_nll(model, evalloop.LLAMA, prime)
     torch.cuda.synchronize()
+    glue = pick_glue(model, prime)
+    if glue['mode'] == 'fused':
+        with torch.no_grad():                               # first-launch set-up of the fused path, outside the warm-up
+            evalloop.sample_nll(model, evalloop.LLAMA, prime)
+        torch.cuda.synchronize()
+    base['config']['glue'] = glue
     # the decoder stack of a step as one CUDA graph (QUIP_NO_GRAPH=1: eager launches, as the roofline replay leg uses)
     stepper = None
     if os.environ.get('QUIP_NO_GRAPH') != '1':
@@ -391,6 +466,13 @@ def main():
             for g in groups:
                 g.dissolve()
             out['decode'] = decode_leg(model, dev, pk)
+            if glue['mode'] == 'fused':                          # the decode step has its own fused variant: check it too
+                try:
+                    ok, worst = decode_glue_ok(model, dev)
+                except Exception as e:
+                    ok, worst = False, repr(e)[:160]
+                os.environ['QUIP_FUSED_LAYER'] = '1' if ok else '0'
+                out['decode']['glue'] = dict(mode='fused' if ok else 'hf', rel_err_vs_torch_glue_step=worst)
             # the reference's benchmark() (opt.py:431-482): token-by-token through the whole HF model with a KV cache
             sec, _ = evalloop.decode_benchmark(model, ids_dev[0][:, :48])
             out['decode']['hf_decode'] = dict(tokens_per_s=1.0 / sec, median_ms_per_token=sec * 1e3, tokens=48,

@@ -1,5 +1,7 @@
 """CPU tests of the fused Llama stack's host logic (quip_b200/fused.py) with the glue ops injected from oracle/glue.py,
 against the HF decoder layers themselves."""
+import os
+
 import pytest
 import torch
 
@@ -113,3 +115,19 @@ def test_decoder_steps_equal_hf_decode_with_kv_cache_on_cpu(nkv, use_ops):
             past = out.past_key_values
             got = dec.step(ids[:, i])
             assert torch.allclose(got, out.logits[:, -1], rtol=2e-4, atol=2e-4), i
+
+
+def test_bench_glue_selection_falls_back_to_hf_and_respects_the_env(monkeypatch):
+    """bench.pick_glue: an explicit QUIP_FUSED_LAYER wins; otherwise the fused stack must run, agree and be faster --
+    on a CPU model the CUDA-only kernels raise, which keeps the HF glue (and says why)."""
+    import bench
+    m = _tiny(torch.float16)
+    ids = torch.randint(0, 199, (1, 32), generator=torch.Generator().manual_seed(1))
+    monkeypatch.setenv('QUIP_FUSED_LAYER', '1')
+    assert bench.pick_glue(m, ids) == dict(mode='fused', chosen_by='QUIP_FUSED_LAYER=1')
+    monkeypatch.setenv('QUIP_FUSED_LAYER', '0')
+    assert bench.pick_glue(m, ids)['mode'] == 'hf'
+    monkeypatch.delenv('QUIP_FUSED_LAYER')
+    info = bench.pick_glue(m, ids)
+    assert info['mode'] == 'hf' and 'CUDA device only' in info['why'] and os.environ['QUIP_FUSED_LAYER'] == '0'
+    monkeypatch.delenv('QUIP_FUSED_LAYER')
