@@ -341,12 +341,20 @@ def main():
     # the decoder stack of a step as one CUDA graph (QUIP_NO_GRAPH=1: eager launches, as the roofline replay leg uses)
     stepper = None
     if os.environ.get('QUIP_NO_GRAPH') != '1':
-        try:
-            stepper = evalloop.enable_graphed_eval(model, evalloop.LLAMA, prime)
-        except Exception as e:
-            print(f'bench: graph capture failed ({e!r}); falling back to eager launches', file=sys.stderr)
-            model._quip_graph_step = None
-            stepper = None
+        for attempt in range(2):
+            try:
+                stepper = evalloop.enable_graphed_eval(model, evalloop.LLAMA, prime)
+                break
+            except Exception as e:
+                model._quip_graph_step = None
+                stepper = None
+                if glue['mode'] == 'fused' and attempt == 0:   # capture the HF-glue step instead
+                    print(f'bench: capture of the fused stack failed ({e!r}); using the HF glue', file=sys.stderr)
+                    os.environ['QUIP_FUSED_LAYER'] = '0'
+                    glue.update(mode='hf', why='capture of the fused stack failed: ' + repr(e)[:160])
+                    continue
+                print(f'bench: graph capture failed ({e!r}); falling back to eager launches', file=sys.stderr)
+                break
     step_fn = stepper if stepper is not None else (lambda ids: evalloop.sample_nll(model, evalloop.LLAMA, ids))
     gen = torch.Generator().manual_seed(1234 + rank)
     total = a.warmup + a.steps
