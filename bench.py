@@ -330,7 +330,7 @@ def main():
     with torch.no_grad():
         prime = torch.randint(0, cfg.vocab_size, (1, SEQ), device=dev)
         for _ in range(2):
-            evalloop.sample_nll(model, evalloop.LLAMA, prime)
+            nll_prime = float(evalloop.sample_nll(model, evalloop.LLAMA, prime))       # HF glue: the reference value below
     torch.cuda.synchronize()
     glue = pick_glue(model, prime)
     if glue['mode'] == 'fused':
@@ -356,6 +356,24 @@ def main():
                 print(f'bench: graph capture failed ({e!r}); falling back to eager launches', file=sys.stderr)
                 break
     step_fn = stepper if stepper is not None else (lambda ids: evalloop.sample_nll(model, evalloop.LLAMA, ids))
+    if glue['mode'] == 'fused' and 'rel_err_vs_hf_layers' in glue:
+        # whole model, end to end: the NLL of the priming sample through the step that will be timed, against the HF-glue
+        # value from the priming pass; a disagreement beyond the perplexity tolerance puts the HF glue back
+        with torch.no_grad():
+            d = abs(float(step_fn(prime)) - nll_prime) / abs(nll_prime)
+        glue['nll_rel_diff_vs_hf_glue'] = d
+        if not d < 1e-3:
+            os.environ['QUIP_FUSED_LAYER'] = '0'
+            glue.update(mode='hf', why='NLL of the fused step differs from the HF-glue step')
+            model._quip_graph_step = None
+            stepper = None
+            if os.environ.get('QUIP_NO_GRAPH') != '1':
+                try:
+                    stepper = evalloop.enable_graphed_eval(model, evalloop.LLAMA, prime)
+                except Exception:
+                    model._quip_graph_step = None
+                    stepper = None
+            step_fn = stepper if stepper is not None else (lambda ids: evalloop.sample_nll(model, evalloop.LLAMA, ids))
     gen = torch.Generator().manual_seed(1234 + rank)
     total = a.warmup + a.steps
     ids_host = torch.randint(0, cfg.vocab_size, (total, 1, SEQ), generator=gen).pin_memory()
