@@ -1,4 +1,4 @@
-"""Smallest possible device check of the staged glue kernels (csrc/glue.cu): a few seconds after `import torch`.
+"""(A script, not a pytest module.)  Smallest possible device check of the staged glue kernels (csrc/glue.cu): a few seconds after `import torch`.
 Appends one JSON line per finished check to gpurun_out/quick_glue.jsonl (flushed as it goes, so a cut-off run still
 leaves what it finished).  No transformers import."""
 import json

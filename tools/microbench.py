@@ -284,10 +284,28 @@ def main():
         lib.quip_config(b'fewtok_max_m', 8)
     if 'glue' in what:
         # glue kernels of csrc/glue.cu against the torch launches they replace, Llama-2-7B sizes at 2048 tokens
-        import sys as _sys
-        _sys.path.insert(0, ROOT)
-        from oracle.glue import TorchGlue            # the torch ops the HF modules issue (timed as the thing replaced)
+        from transformers.models.llama import modeling_llama as ML
         from quip_b200.fused import CudaGlue
+
+        class HFGlue:                                 # the HF modules themselves: what the kernels replace
+            def rmsnorm(self, x, weight, eps, residual=None):
+                norm = ML.LlamaRMSNorm(x.shape[-1], eps=eps).to(x.device, x.dtype)
+                norm.weight.data = weight
+                if residual is None:
+                    return norm(x)
+                s = residual + x
+                return s, norm(s)
+
+            def rope_(self, q, k, cos, sin, head_dim):
+                S_ = q.shape[1]
+                qh = q.view(1, S_, -1, head_dim).transpose(1, 2)
+                kh = k.view(1, S_, -1, head_dim).transpose(1, 2)
+                return ML.apply_rotary_pos_emb(qh, kh, cos[None], sin[None])
+
+            def silu_mul(self, gate, up):
+                return torch.nn.functional.silu(gate) * up
+
+        TorchGlue = HFGlue
         S, d, inter, nh, hd = 2048, 4096, 11008, 32, 128
         cg, tg = CudaGlue(), TorchGlue()
         cp = 24                                       # rotate over > L2 of distinct buffers
