@@ -164,6 +164,53 @@ def decode_leg(model, dev, pk):
                 roofline_tokens_per_s=pk['hbm_gbs'] * 1e9 / nbytes)
 
 
+def contraction_leg(dev, pk):
+    """The packed contraction alone in steady state: one token (and two) against the 2-bit gate/up/down-sized matrices of
+    all 32 layers stacked into one (352256 x 4096) matrix, so the launch ramp is amortised and every packed word comes from
+    HBM (360 MB per matrix, two matrices alternated).  Algorithmic bytes = packed codes + fp16 activations in and out
+    (SURVEY section 8d B_codes); this is the figure the north star's ">= 70 % of the HBM roofline" refers to."""
+    from quip_b200 import _lib
+    from quip_b200.quant import packed_words
+    lib = _lib.load()
+    N, K, bits, copies = 32 * 11008, 4096, 2, 2
+    qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (copies, packed_words(N, K, bits)), dtype=torch.int32, device=dev)
+    sc = torch.full((N,), 0.01, device=dev)
+    ze = sc * 1.5
+    res = {}
+    for M in (1, 2):
+        x = torch.randn(M, K, device=dev).half()
+        z = torch.empty(M, N, dtype=torch.float16, device=dev)
+        descs = []
+        for c in range(copies):
+            d = _lib.QuipLinearDesc()
+            d.K, d.N, d.bits, d.flags = K, N, bits, _lib.QUIP_FLAG_SYMMETRIC
+            d.qweight, d.scales, d.zeros = qw[c].data_ptr(), sc.data_ptr(), ze.data_ptr()
+            descs.append(d)
+        need = C.c_size_t()
+        _lib.check(lib.quip_qlinear_workspace_bytes(C.byref(descs[0]), M, C.byref(need)))
+        ws = torch.zeros(max(need.value, 1 << 20), dtype=torch.uint8, device=dev)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def run(i):
+            _lib.check(lib.quip_qgemm(C.byref(descs[i % copies]), _lib.ptr(x), None, None, _lib.ptr(z), M, 1,
+                                      _lib.ptr(ws), ws.numel(), st))
+        for i in range(4):
+            run(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for i in range(reps):
+            run(i)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) / reps * 1e3
+        nbytes = N * K * bits / 8 + 2 * M * K + 2 * M * N
+        res[str(M)] = dict(us=us, gbs=nbytes / us / 1e3, hbm_frac=nbytes / us / 1e3 / pk['hbm_gbs'])
+    return dict(what='quip_qgemm, 2-bit, (352256 x 4096) stacked matrix, tokens -> {us, GB/s of codes + activations, fraction of '
+                     'the measured HBM peak}', kernel='qgemv_i8_stream_kernel (int8 tensor-core GEMV, three-limb tokens)', tokens=res)
+
+
 def pick_glue(model, prime):
     """Which glue runs between the packed linears of a decoder layer in this run: the HF modules' own torch launches, or the
     fused kernels of csrc/glue.cu (quip_b200/fused.py).  QUIP_FUSED_LAYER=0/1 forces one; otherwise both are run here on
@@ -499,6 +546,10 @@ def main():
                     ok, worst = False, repr(e)[:160]
                 os.environ['QUIP_FUSED_LAYER'] = '1' if ok else '0'
                 out['decode']['glue'] = dict(mode='fused' if ok else 'hf', rel_err_vs_torch_glue_step=worst)
+            try:
+                out['decode']['contraction_kernel'] = contraction_leg(dev, pk)
+            except Exception as e:
+                out['decode']['contraction_kernel'] = dict(error=repr(e)[:160])
             # the reference's benchmark() (opt.py:431-482): token-by-token through the whole HF model with a KV cache
             sec, _ = evalloop.decode_benchmark(model, ids_dev[0][:, :48])
             out['decode']['hf_decode'] = dict(tokens_per_s=1.0 / sec, median_ms_per_token=sec * 1e3, tokens=48,
