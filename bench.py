@@ -16,6 +16,11 @@ linears each -> final norm -> lm_head -> CE loss), i.e. one pass of llama_eval's
           copies its ids from pinned host memory and reads the scalar result back.
   roofline  the dominant kernel (tcgen05 packed GEMM): algorithmic flops of its launches / their summed
           device time, measured with CUDA events around every launch inside the timed region.
+  config.glue  which glue ran between the packed linears (HF torch launches or the fused kernels of csrc/glue.cu), chosen
+          in the run by `pick_glue` -- both paths on two real layers, fused only if it agrees within 1e-3 and is faster,
+          then the whole-model NLL of the step to be timed is compared with the HF-glue value.
+  decode  extras, N=1 only: the 224 QuantLinear calls of one token from a CUDA graph, the packed contraction alone in
+          steady state against the HBM peak, eager HF decode, graph decode and its batch sweep.
   cpu_baseline / --impl reference: the reference's effective path (HF decoder layer with dense fp16
           weights, the per-layer loop of llama.py:174-253 ported in oracle/evalloop.py) on the host cores,
           on a bounded sample (1 decoder layer x 1 sample), extrapolated to 32 layers.
