@@ -216,6 +216,20 @@ def contraction_leg(dev, pk):
                      'the measured HBM peak}', kernel='qgemv_i8_stream_kernel (int8 tensor-core GEMV, three-limb tokens)', tokens=res)
 
 
+def _device_ms(fn, reps, warm):
+    """Average device milliseconds of fn() over `reps` calls (CUDA events on the current stream)."""
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
 def pick_glue(model, prime):
     """Which glue runs between the packed linears of a decoder layer in this run: the HF modules' own torch launches, or the
     fused kernels of csrc/glue.cu (quip_b200/fused.py).  QUIP_FUSED_LAYER=0/1 forces one; otherwise both are run here on
@@ -246,18 +260,7 @@ def pick_glue(model, prime):
 
             ref, got = hf().float(), fu().float()
             err = float((got - ref).norm() / ref.norm())
-            times = {}
-            for name, fn in (('hf', hf), ('fused', fu)):
-                for _ in range(2):
-                    fn()
-                torch.cuda.synchronize()
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                for _ in range(3):
-                    fn()
-                e1.record()
-                torch.cuda.synchronize()
-                times[name] = e0.elapsed_time(e1) / 3 / len(layers)
+            times = {name: _device_ms(fn, reps=3, warm=2) / len(layers) for name, fn in (('hf', hf), ('fused', fu))}
             info.update(rel_err_vs_hf_layers=err, ms_per_layer_hf=times['hf'], ms_per_layer_fused=times['fused'],
                         note='eager launches, first two decoder layers, one 2048-token sample')
             if err < 1e-3 and times['fused'] < times['hf']:

@@ -131,3 +131,69 @@ def test_bench_glue_selection_falls_back_to_hf_and_respects_the_env(monkeypatch)
     info = bench.pick_glue(m, ids)
     assert info['mode'] == 'hf' and 'CUDA device only' in info['why'] and os.environ['QUIP_FUSED_LAYER'] == '0'
     monkeypatch.delenv('QUIP_FUSED_LAYER')
+
+
+def test_bench_glue_selection_happy_path_with_injected_kernels(monkeypatch):
+    """The decision logic of bench.pick_glue with the torch restatement standing in for the CUDA kernels and a fake
+    device timer: fused is chosen only when it agrees with the HF layers AND is faster."""
+    import bench
+    from quip_b200 import fused
+    m = _tiny(torch.float16)
+    ids = torch.randint(0, 199, (1, 32), generator=torch.Generator().manual_seed(1))
+    monkeypatch.setattr(fused, 'CudaGlue', TorchGlue)
+    clock = {'calls': 0}
+
+    def fake_timer(fn, reps, warm):
+        fn()
+        clock['calls'] += 1
+        return clock['ms'][clock['calls'] - 1]
+
+    monkeypatch.setattr(bench, '_device_ms', fake_timer)
+    monkeypatch.delenv('QUIP_FUSED_LAYER', raising=False)
+    clock.update(calls=0, ms=[4.0, 2.0])                                  # hf, fused: fused faster
+    info = bench.pick_glue(m, ids)
+    assert info['mode'] == 'fused' and info['rel_err_vs_hf_layers'] < 1e-3 and os.environ['QUIP_FUSED_LAYER'] == '1'
+    assert info['ms_per_layer_hf'] == 2.0 and info['ms_per_layer_fused'] == 1.0          # per layer: two layers timed
+    monkeypatch.delenv('QUIP_FUSED_LAYER')
+    clock.update(calls=0, ms=[2.0, 4.0])                                  # fused slower: keep the HF glue
+    assert bench.pick_glue(m, ids)['mode'] == 'hf' and os.environ['QUIP_FUSED_LAYER'] == '0'
+    monkeypatch.delenv('QUIP_FUSED_LAYER')
+
+    class WrongGlue(TorchGlue):                                            # a kernel that disagrees: rejected however fast
+        def silu_mul(self, gate, up):
+            return gate * up
+
+    monkeypatch.setattr(fused, 'CudaGlue', WrongGlue)
+    clock.update(calls=0, ms=[4.0, 1.0])
+    info = bench.pick_glue(m, ids)
+    assert info['mode'] == 'hf' and info['rel_err_vs_hf_layers'] > 1e-3
+    monkeypatch.delenv('QUIP_FUSED_LAYER')
+
+
+def test_bench_decode_glue_check_logic(monkeypatch):
+    import bench
+    from quip_b200 import fused
+    m = _tiny(torch.float32)
+    m.half = lambda: m                                                   # keep fp32: CPU half matmuls are slow and noisy
+    monkeypatch.setattr(fused, 'CudaGlue', TorchGlue)
+    import quip_b200.decode as dec
+    orig = dec.GraphDecoder.__init__
+
+    def init32(self, *a, **kw):                                          # the decoder keeps fp16 tables for the GPU path
+        orig(self, *a, **kw)
+        cos, sin = m.model.rotary_emb(torch.zeros(1, 1, 128), torch.arange(self.max_len)[None, :])
+        self.cos, self.sin = cos[0].contiguous(), sin[0].contiguous()
+        self.k_cache, self.v_cache = self.k_cache.float(), self.v_cache.float()
+
+    monkeypatch.setattr(dec.GraphDecoder, '__init__', init32)
+    ok, worst = bench.decode_glue_ok(m, torch.device('cpu'))
+    assert ok and worst < 1e-4
+
+    class WrongGlue(TorchGlue):
+        def silu_mul(self, gate, up):
+            return gate * up
+
+    monkeypatch.setattr(fused, 'CudaGlue', WrongGlue)
+    ok, worst = bench.decode_glue_ok(m, torch.device('cpu'))
+    assert not ok and worst > 2e-3
+    monkeypatch.delenv('QUIP_FUSED_LAYER', raising=False)
