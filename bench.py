@@ -417,7 +417,8 @@ def main():
         with torch.no_grad():
             d = abs(float(step_fn(prime)) - nll_prime) / abs(nll_prime)
         glue['nll_rel_diff_vs_hf_glue'] = d
-        if not d < 1e-3:
+        # the loss is an fp16 number (opt.py:292-294: CrossEntropy on fp16 logits), so d moves in steps of ~7.5e-4: allow two
+        if not d < 2e-3:
             os.environ['QUIP_FUSED_LAYER'] = '0'
             glue.update(mode='hf', why='NLL of the fused step differs from the HF-glue step')
             model._quip_graph_step = None
