@@ -365,6 +365,8 @@ def main():
     from quip_b200 import _lib, evalloop, pipeline
     from quip_b200.llama import llama_eval
     from quip_b200.synth import LLAMA2_7B, build_synthetic_model
+    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
+        os.environ['NCCL_DEBUG'] = 'WARN'                   # NCCL prints its version banner on stdout: keep stdout to the one JSON line
     pipeline.init_distributed()
     import torch.distributed as dist
     local = int(os.environ.get('LOCAL_RANK', '0'))
