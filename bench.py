@@ -365,8 +365,9 @@ def main():
     from quip_b200 import _lib, evalloop, pipeline
     from quip_b200.llama import llama_eval
     from quip_b200.synth import LLAMA2_7B, build_synthetic_model
-    if os.environ.get('NCCL_DEBUG', '').upper() == 'VERSION':
-        os.environ['NCCL_DEBUG'] = 'WARN'                   # NCCL prints its version banner on stdout: keep stdout to the one JSON line
+    # NCCL writes its debug output (the version banner at NCCL_DEBUG=VERSION/WARN) to stdout: send it to stderr so that
+    # stdout carries the one JSON line only
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')
     pipeline.init_distributed()
     import torch.distributed as dist
     local = int(os.environ.get('LOCAL_RANK', '0'))
