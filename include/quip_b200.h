@@ -102,8 +102,8 @@ int quip_qlinear_workspace_bytes(const QuipLinearDesc* d, int64_t M, size_t* out
 
 /* Building blocks (also exported for tests and micro-benchmarks). */
 /* z (M,N) fp16 = x2 (M,K) fp16 contracted with the packed matrix + affine epilogue (+bias if given).
- * xsum (M) fp32 row sums of x2, required unless QUIP_FLAG_SYMMETRIC.  path: 0 auto, 1 mma.sync skinny
- * kernel, 2 tcgen05 kernel, 3 tcgen05 2-CTA (cta_group::2) kernel, 4 tcgen05 TS-mode kernel (weights in
+ * xsum (M) fp32 row sums of x2, required unless QUIP_FLAG_SYMMETRIC.  path: 0 auto, 1 few-token kernels (32-token
+ * chunks; needs the workspace), 2 tcgen05 kernel, 3 tcgen05 2-CTA (cta_group::2) kernel, 4 tcgen05 TS-mode kernel (weights in
  * TMEM, 2-bit only). */
 int quip_qgemm(const QuipLinearDesc* d, const void* x2, const float* xsum, const void* bias,
                void* z, int64_t M, int path, void* workspace, size_t workspace_bytes, void* stream);

@@ -100,7 +100,10 @@ static WsPlan plan_ws(const QuipLinearDesc* d, int64_t M) {
   p.zbuf = off; if (u_on) off += xn;
   p.bufC = off; if (u_on) off += xn;
   p.part = off;
-  if (M <= SKINNY_MAX_M) off += align_up(skinny_workspace_bytes(d->N, (int)M, skinny_pick_ksplit(d->N, d->K, 64, (int)M)), 256);
+  // split-K partials of the few-token contraction: for M itself when it is small, else for one 32-token chunk (quip_qgemm
+  // path 1 walks a larger M in chunks)
+  const int mc = M <= SKINNY_MAX_M ? (int)M : SKINNY_MAX_M;
+  off += align_up(skinny_workspace_bytes(d->N, mc, skinny_pick_ksplit(d->N, d->K, 64, mc)), 256);
   p.total = off;
   return p;
 }
@@ -250,7 +253,8 @@ extern "C" int quip_qgemm(const QuipLinearDesc* d, const void* x2, const float* 
   QUIP_CHECK_ARG(x2 && z && M > 0 && M < (1ll << 31), "bad arguments");
   WsPlan p = plan_ws(d, M);
   QUIP_CHECK_ARG(path >= 0 && path <= 4, "path must be 0..4");
-  if ((path == 1 || (path == 0 && M <= SKINNY_MAX_M)) && M <= SKINNY_MAX_M) {
+  // the few-token kernels keep split-K partials + arrival counters in the workspace (path 1 loops 32-token chunks for any M)
+  if (path == 1 || (path == 0 && M <= SKINNY_MAX_M)) {
     if (!workspace || workspace_bytes < p.total) {
       set_error("workspace too small: need %zu bytes, have %zu", p.total, workspace_bytes);
       return QUIP_ERR_WORKSPACE;

@@ -98,8 +98,9 @@ def supports(model, h, kwargs):
     return hd % 16 == 0 and cfg.hidden_size % 8 == 0 and cfg.intermediate_size % 8 == 0
 
 
-def llama_stack(layers, h, kwargs, ops=None):
-    """`for layer in layers: h = layer(h, **kwargs)` for LlamaDecoderLayers on one sample h (1, S, hidden)."""
+def llama_stack(layers, h, kwargs, ops=None, trace=None):
+    """`for layer in layers: h = layer(h, **kwargs)` for LlamaDecoderLayers on one sample h (1, S, hidden).  `trace`: an optional
+    list that receives (layer index, stage name, tensor) for tools/glue_bisect.py."""
     ops = ops or CudaGlue()
     cos, sin = kwargs['position_embeddings']
     cos, sin = cos[0].contiguous(), sin[0].contiguous()                     # (S, head_dim)
@@ -108,7 +109,12 @@ def llama_stack(layers, h, kwargs, ops=None):
     pend = None                        # previous layer's MLP output, not yet added to h
     x = None
     h = h.contiguous()
-    for layer in layers:
+
+    def rec(li, name, t):
+        if trace is not None:
+            trace.append((li, name, t.clone()))
+
+    for li, layer in enumerate(layers):
         a, mlp = layer.self_attn, layer.mlp
         n1, n2 = layer.input_layernorm, layer.post_attention_layernorm
         hd = a.head_dim
@@ -116,22 +122,40 @@ def llama_stack(layers, h, kwargs, ops=None):
             x = ops.rmsnorm(h, n1.weight, n1.variance_epsilon)
         else:
             h, x = ops.rmsnorm(h, n1.weight, n1.variance_epsilon, residual=pend)
+        rec(li, 'h_in', h)
+        rec(li, 'x_attn', x)
         q, k, v = a.q_proj(x), a.k_proj(x), a.v_proj(x)                     # sibling groups launch these concurrently
+        for nm, t in (('q_lin', q), ('k_lin', k), ('v_lin', v)):
+            rec(li, nm, t)
         ops.rope_(q, k, cos, sin, hd)
+        rec(li, 'q_rope', q)
+        rec(li, 'k_rope', k)
         nq, nkv = q.shape[-1] // hd, k.shape[-1] // hd
         qh = q.view(1, S, nq, hd).transpose(1, 2)
         kh = k.view(1, S, nkv, hd).transpose(1, 2)
         vh = v.view(1, S, nkv, hd).transpose(1, 2)
         extra = {}
-        if nkv != nq:                                                       # as transformers' sdpa_attention_forward
-            if mask is None:
-                extra['enable_gqa'] = True
-            else:
-                kh = kh.repeat_interleave(nq // nkv, dim=1)
-                vh = vh.repeat_interleave(nq // nkv, dim=1)
+        # the same call transformers' sdpa_attention_forward makes (enable_gqa whenever there is no mask, also for
+        # nkv == nq), so that torch picks the same SDPA backend for both glues
+        if mask is None:
+            extra['enable_gqa'] = True
+        elif nkv != nq:
+            kh = kh.repeat_interleave(nq // nkv, dim=1)
+            vh = vh.repeat_interleave(nq // nkv, dim=1)
         o = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=mask, dropout_p=0.0, scale=a.scaling,
                                            is_causal=(mask is None and S > 1), **extra)
         o = o.transpose(1, 2).reshape(1, S, nq * hd).contiguous()
-        h, x = ops.rmsnorm(h, n2.weight, n2.variance_epsilon, residual=a.o_proj(o))
-        pend = mlp.down_proj(ops.silu_mul(mlp.gate_proj(x), mlp.up_proj(x)))
+        rec(li, 'attn_out', o)
+        ao = a.o_proj(o)
+        rec(li, 'o_lin', ao)
+        h, x = ops.rmsnorm(h, n2.weight, n2.variance_epsilon, residual=ao)
+        rec(li, 'h_mid', h)
+        rec(li, 'x_mlp', x)
+        g, u = mlp.gate_proj(x), mlp.up_proj(x)
+        rec(li, 'gate', g)
+        rec(li, 'up', u)
+        act = ops.silu_mul(g, u)
+        rec(li, 'act', act)
+        pend = mlp.down_proj(act)
+        rec(li, 'down', pend)
     return h if pend is None else h + pend

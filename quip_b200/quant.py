@@ -281,6 +281,7 @@ class SiblingGroup:
         self.members = list(members)
         self.streams = None
         self._key = None
+        self._x = None
         self._outs = [None] * len(self.members)
         self._events = [None] * len(self.members)
         for i, m in enumerate(self.members):
@@ -289,10 +290,16 @@ class SiblingGroup:
     def dissolve(self):
         for m in self.members:
             m._group, m._group_index = None, 0
+        self._x, self._key = None, None
+        self._outs = [None] * len(self.members)
 
     def get(self, index, x):
-        key = (id(x), x.data_ptr(), tuple(x.shape), x._version)
-        if key != self._key or self._outs[index] is None:
+        # the pending input is held by a strong reference and compared by identity: its id / address cannot be reused by a
+        # different tensor while sibling outputs are pending
+        key = (x.data_ptr(), tuple(x.shape), x._version)
+        if x is not self._x or key != self._key or self._outs[index] is None:
+            self._outs = [None] * len(self.members)         # outputs of an abandoned input are dropped
+            self._x = x
             dev = x.device
             if self.streams is None or self.streams[0].device != dev:
                 self.streams = [torch.cuda.Stream(device=dev) for _ in self.members[1:]]
@@ -320,6 +327,8 @@ class SiblingGroup:
             self._key = key
         y, ev = self._outs[index], self._events[index]
         self._outs[index] = None
+        if all(o is None for o in self._outs):
+            self._x = None                                  # every sibling consumed: release the input
         if ev is not None:
             cur = torch.cuda.current_stream(x.device)
             cur.wait_event(ev)
@@ -449,9 +458,39 @@ class QuantLinear(nn.Module):
         return unpack_codes(self.qweight, self.outfeatures, self.infeatures, self.bits)
 
     # -- C ABI descriptor ----------------------------------------------------------------------
+    # dtypes the C ABI reads the buffers as (include/quip_b200.h): a blanket model.half() / .float() / .to(dtype) must not
+    # change them -- the kernels would reinterpret the bytes
+    _BUFFER_DTYPES = dict(qweight=torch.int32, meta=torch.int32, v_idx=torch.int32, u_idx=torch.int32, scales=torch.float32,
+                          zeros=torch.float32, inv_scale=torch.float32, bias=torch.float16, v_f0=torch.float16,
+                          v_f1=torch.float16, u_f0=torch.float16, u_f1=torch.float16)
+
     def _apply(self, fn, *a, **kw):
         self._desc = None
-        return super()._apply(fn, *a, **kw)
+        out = super()._apply(fn, *a, **kw)
+        for name, dt in self._BUFFER_DTYPES.items():
+            buf = self._buffers.get(name)
+            if buf is not None and buf.dtype != dt:
+                self._buffers[name] = buf.to(dt)
+        return out
+
+    # the cached descriptor holds ctypes pointers into this module's buffers: copies and pickles rebuild it lazily
+    _TRANSIENT = ('_desc', '_desc_ref', '_frag_keep', '_u_inv', '_ws_need', 'meta_host')
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        for k in self._TRANSIENT:
+            st.pop(k, None)
+        st['_desc'] = None
+        st['_group'], st['_group_index'] = None, 0
+        return st
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
     def _load_from_state_dict(self, *a, **kw):
         self._desc = None                       # cached host copies (meta, fragment-order factors, inverse index) are stale
@@ -496,6 +535,10 @@ class QuantLinear(nn.Module):
         if self._desc is None:
             self.meta_host = self.meta.tolist()
             self._frag_keep = {}
+            for name, dt in self._BUFFER_DTYPES.items():
+                buf = self._buffers.get(name)
+                if buf is not None and buf.dtype != dt:
+                    raise TypeError(f'QuantLinear buffer {name!r} is {buf.dtype}, the packed kernels read it as {dt}')
             d = _lib.QuipLinearDesc()
             d.K, d.N, d.bits = self.infeatures, self.outfeatures, self.bits
             d.flags = _lib.QUIP_FLAG_SYMMETRIC if self.meta_host[1] else 0

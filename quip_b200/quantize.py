@@ -312,8 +312,8 @@ def options_from_args(args):
     if g('incoh_processing', False):
         pre_gptqH = pre_rescale = pre_proj = True
         qfn = 'b'
-    if quant == 'nearest':
-        pre_gptqH = False                                 # Nearest has no preproc call (near.py:8-22)
+    # preproc runs for every method, nearest included (opt.py:154-157): dead-column zeroing (method.py:185-187) applies
+    # there too; the damping of H is harmless because nearest ignores H
     return dict(bits=g('wbits'), method=_METHODS[quant], greedy_passes=g('npasses', 0), qfn=qfn, rescale=bool(pre_rescale),
                 incoh=_PROJ[g('pre_proj_extra', 0)] if pre_proj else None, percdamp=g('percdamp', 0.01), damp=bool(pre_gptqH))
 

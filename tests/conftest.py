@@ -87,3 +87,21 @@ def load_tiny_opt():
                                  bias=torch.from_numpy(z[p + 'bias']) if (p + 'bias') in z.files else None,
                                  scaleWH=torch.from_numpy(z[p + 'scaleWH']), U=bf('U', N), V=bf('V', K))
     return model, parts, torch.from_numpy(z['test_ids']), float(z['ppl'])
+
+
+def load_big_layer(name='big_4096'):
+    """Golden 4096 x 4096 layer quantized by the live reference (oracle/gen_golden_big.py) -> (LayerParts, npz)."""
+    import numpy as np
+    import torch
+    from quip_b200.capture import Butterfly, LayerParts
+    z = np.load(os.path.join(GOLDEN, f'layer_{name}.npz'))
+    N, K = int(z['N']), int(z['K'])
+    p = z['codes2'][..., None] >> np.array([0, 2, 4, 6], dtype=np.uint8)
+    codes = (p & 3).reshape(N, K).astype(np.uint8)
+
+    def bf(s, n):
+        return Butterfly(n, torch.from_numpy(z[s + '_B0']), torch.from_numpy(z[s + '_B1']),
+                         torch.from_numpy(z[s + '_p_in']).long(), torch.from_numpy(z[s + '_p_out']).long())
+    tp = LayerParts(bits=2, qfn='b', codes=torch.from_numpy(codes), scales=torch.from_numpy(z['scales']),
+                    zeros=torch.from_numpy(z['zeros']), scaleWH=torch.from_numpy(z['scaleWH']), U=bf('U', N), V=bf('V', K))
+    return tp, z

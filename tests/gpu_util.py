@@ -72,40 +72,28 @@ def run_qgemm(codes, scales, zeros, bits, X, path, bias=None, symmetric=False):
 
 
 def torch_reference_forward(ql, x):
-    """fp32 restatement of QuantLinear.forward in plain torch, from the module's own buffers and pass descriptors:
-    y = gather_u(passes_u(passes_v(gather_v(x * 1/s)) @ Q^T)) + bias, Q = scales * codes - zeros.  No fp16 rounding
-    between the stages: the CUDA path must agree within the fp16 error budget."""
-    d = ql._descriptor()
-    K, N = ql.infeatures, ql.outfeatures
-    dev = x.device
+    """fp32 restatement of QuantLinear.forward in plain torch (quip_b200/selfcheck.py, shared with bench.py's self-check)."""
+    from quip_b200.selfcheck import restated_forward
+    return restated_forward(ql, x)
 
-    def side(sd, h, name):
-        n = sd.n
-        for i in range(sd.npass if n else 0):
-            ps = sd.passes[i]
-            F_ = getattr(ql, f'{name}_f{i}').float()
-            p, nblk = ps.p, ps.nblk
-            if F_.shape[0] == 1 and nblk > 1:
-                F_ = F_.expand(nblk, p, p)
-            if ps.strided:
-                h3 = h.reshape(-1, p, nblk)                                   # element j of block b at j*nblk + b
-                h = torch.einsum('bij,mjb->mib', F_, h3).reshape(-1, n)
-            else:
-                h3 = h.reshape(-1, nblk, p)
-                h = torch.einsum('bij,mbj->mbi', F_, h3).reshape(-1, n)
-        return h
 
-    h = x.float().reshape(-1, K)
-    if d.V.n or d.inv_scale:
-        idx = ql.v_idx.long() if (d.V.n and d.V.idx) else torch.arange(K, device=dev)
-        h = h[:, idx] * (ql.inv_scale.float()[idx] if d.inv_scale else 1.0)
-    h = side(d.V, h, 'v')
-    codes = Q.unpack_codes(ql.qweight, N, K, ql.bits).float()
-    Qm = ql.scales.float().reshape(-1, 1) * codes - ql.zeros.float().reshape(-1, 1)
-    z = h @ Qm.T
-    z = side(d.U, z, 'u')
-    if d.U.n and d.U.idx:
-        z = z[:, ql.u_idx.long()]
-    if ql.bias is not None:
-        z = z + ql.bias.float()
+def run_qgemm_dev(codes, scales, zeros, bits, x, path, bias=None, symmetric=False):
+    """quip_qgemm on DEVICE tensors (the Llama-sized cases: nothing goes through numpy).  codes (N, K) uint8, scales / zeros
+    (N) fp32, x (M, K) fp16, bias (N) fp16 or None -> z (M, N) fp16 on the device."""
+    lib = _lib.load()
+    N, K = codes.shape
+    M = x.shape[0]
+    qw = Q.pack_codes(codes, bits)
+    d = _lib.QuipLinearDesc()
+    d.K, d.N, d.bits, d.flags = K, N, bits, (_lib.QUIP_FLAG_SYMMETRIC if symmetric else 0)
+    d.qweight, d.scales, d.zeros = qw.data_ptr(), scales.data_ptr(), zeros.data_ptr()
+    need = C.c_size_t()
+    _lib.check(lib.quip_qlinear_workspace_bytes(C.byref(d), M, C.byref(need)))
+    ws = torch.zeros(max(need.value, 1 << 20), dtype=torch.uint8, device=x.device)
+    xsum = torch.empty(M, dtype=torch.float32, device=x.device)
+    _lib.check(lib.quip_rowsum(_lib.ptr(x), _lib.ptr(xsum), M, K, stream()))
+    z = torch.full((M, N), float('nan'), dtype=torch.float16, device=x.device)
+    _lib.check(lib.quip_qgemm(C.byref(d), _lib.ptr(x), _lib.ptr(xsum), _lib.ptr(bias), _lib.ptr(z), M, path,
+                              _lib.ptr(ws), ws.numel(), stream()))
+    torch.cuda.synchronize()
     return z
