@@ -259,7 +259,10 @@ int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, in
                   (void*)&in_scale, (void*)&out_inv, (void*)&out_bias, (void*)&nb_cta};
   const void* kern = M <= 8 ? (const void*)pass_fewtok_kernel<1>
                             : (M <= 16 ? (const void*)pass_fewtok_kernel<2> : (const void*)pass_fewtok_kernel<4>);
-  if (smem > 48 * 1024) {                                  // many tokens x two 688-wide blocks: opt in once per device
+  // the kernel also holds NG x FT_WARPS x 16 x 9 floats of static shared memory (the k-part reduction): the 48 KiB default
+  // limit applies to the sum
+  const size_t smem_static = (size_t)(M <= 8 ? 1 : (M <= 16 ? 2 : 4)) * FT_WARPS * 16 * 9 * sizeof(float);
+  if (smem + smem_static > 48 * 1024) {                    // many tokens x two 688-wide blocks: opt in once per device
     QUIP_CHECK_ARG(smem <= 200 * 1024, "few-token pass: %zu bytes of token staging", smem);
     static bool attr_done[64][3] = {};
     int dev = 0;

@@ -10,8 +10,9 @@ two ways:
     evaluates samples rank, rank+G, ...; the only collective is one all-reduce of (sum NLL, tokens).
   * layer pipeline (`pp_eval`), for models that do not fit one GPU: contiguous layer ranges per rank
     exactly as opt.py:424-426 (or --layers-dist, llama.py:400-413), micro-batch = one sample, hidden
-    states (1,S,H) fp16 sent to the next stage with isend/irecv (ncclSend/ncclRecv over NVLink),
-    receives posted one sample ahead so the transfer of sample j+1 overlaps the compute of sample j.
+    states (1,S,H) fp16 sent to the next stage with isend/irecv (ncclSend/ncclRecv over NVLink) on one
+    communicator per link, receives posted one sample ahead and sends double-buffered so transfers overlap
+    the layers; each stage's body is one CUDA-graph replay per sample (`PipelineStage`).
 """
 import os
 
@@ -80,9 +81,110 @@ def place_stage(model, arch, lo, hi, dev, first, last):
         arch.head(model).to(dev)
 
 
+_pair_groups = {}
+
+
+def pair_groups():
+    """One process group per adjacent stage pair (r, r+1).  Point-to-point operations on the default group are serialised
+    with every other operation on it (NCCL warns about exactly that); with a communicator per link a stage's receive from
+    r-1, its send to r+1 and the next receive run independently of each other and of the final all-reduce."""
+    world = dist.get_world_size()
+    key = (world, dist.get_backend())
+    if key not in _pair_groups:
+        _pair_groups[key] = [dist.new_group([r, r + 1]) for r in range(world - 1)]      # same order on every rank
+    return _pair_groups[key]
+
+
+class PipelineStage:
+    """One rank's contiguous layer range (opt.py:424-426) as a pipeline stage over fixed-length samples.
+
+    * the layer kwargs (mask / positions / rotary tables) are derived ONCE from an example batch -- they are the same for
+      every sample of that length -- instead of re-running the embedding front end on every stage for every sample;
+    * the stage body (its decoder layers; on the last stage also final norm -> lm_head -> loss) is captured in one CUDA
+      graph on CUDA devices and replayed per sample (eager on CPU: the gloo tests);
+    * hidden states travel over per-link process groups; the receive of sample j+1 is posted before sample j is computed
+      and sends are double-buffered, so transfers overlap the layers.
+    """
+
+    def __init__(self, model, arch, lo, hi, dev, example_batch, graph=None):
+        self.model, self.arch, self.dev = model, arch, torch.device(dev)
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.first, self.last = self.rank == 0, self.rank == self.world - 1
+        self.layers = [arch.layers(model)[i] for i in range(lo, hi)]
+        self.groups = pair_groups()
+        self.seqlen = example_batch.shape[1]
+        with torch.no_grad():
+            h0, self.kw = evalloop.layer_inputs(model, arch, example_batch.to(self.dev))
+        self.h_in = torch.zeros_like(h0)
+        self.labels = example_batch.to(self.dev).clone()
+        self.recv_bufs = [torch.empty_like(h0) for _ in range(2)]
+        self.send_bufs = [torch.empty_like(h0) for _ in range(2)]
+        self.graph = None
+        use_graph = self.dev.type == 'cuda' if graph is None else graph
+        if use_graph:
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.no_grad(), torch.cuda.stream(side):
+                for _ in range(2):                          # lazy set-up (descriptors, workspaces) outside the graph
+                    self._body()
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph, stream=side, capture_error_mode='thread_local'):
+                    self.out = self._body()
+            torch.cuda.current_stream(self.dev).wait_stream(side)
+
+    def _body(self):
+        h = evalloop.run_layers(self.model, self.arch, self.layers, self.h_in, self.kw)
+        if self.last:
+            return evalloop.sample_logits_nll(self.model, self.arch, h, self.labels, self.model.seqlen)
+        return h
+
+    def _compute(self):
+        if self.graph is not None:
+            self.graph.replay()
+            return self.out
+        return self._body()
+
+    @torch.no_grad()
+    def run(self, batches):
+        """All samples of `batches` (an indexable of (1, S) id tensors, host or device) through this stage.  Returns the summed
+        NLL on the last stage (0 elsewhere)."""
+        n = len(batches)
+        nll = torch.zeros((), dtype=torch.float32, device=self.dev)
+        recv = [None, None]
+        sends = [None, None]
+        g_in = self.groups[self.rank - 1] if not self.first else None
+        g_out = self.groups[self.rank] if not self.last else None
+        if not self.first and n:
+            recv[0] = dist.irecv(self.recv_bufs[0], src=self.rank - 1, group=g_in)
+        for j in range(n):
+            if self.first:
+                h0, _ = evalloop.layer_inputs(self.model, self.arch, batches[j].to(self.dev, non_blocking=True))
+                self.h_in.copy_(h0)
+            else:
+                if j + 1 < n:                                 # next receive in flight while this sample is computed
+                    recv[(j + 1) & 1] = dist.irecv(self.recv_bufs[(j + 1) & 1], src=self.rank - 1, group=g_in)
+                recv[j & 1].wait()
+                self.h_in.copy_(self.recv_bufs[j & 1])
+            if self.last:
+                self.labels.copy_(batches[j].to(self.dev, non_blocking=True))
+            out = self._compute()
+            if self.last:
+                nll += out
+            else:
+                if sends[j & 1] is not None:
+                    sends[j & 1].wait()                       # the buffer's previous send (sample j-2) has left
+                self.send_bufs[j & 1].copy_(out)
+                sends[j & 1] = dist.isend(self.send_bufs[j & 1], dst=self.rank + 1, group=g_out)
+        for r in sends:
+            if r is not None:
+                r.wait()
+        return nll
+
+
 @torch.no_grad()
-def pp_eval(model, arch, testenc, dev, layers_dist=None, verbose=False):
-    """Layer-pipelined perplexity over all ranks of the default process group."""
+def pp_eval(model, arch, testenc, dev, layers_dist=None, verbose=False, graph=None):
+    """Layer-pipelined perplexity over all ranks of the default process group (reference placement rule opt.py:424-426 /
+    --layers-dist llama.py:400-413; NCCL send/recv between neighbours instead of `.to(device)` hops)."""
     ids = testenc.input_ids if hasattr(testenc, 'input_ids') else testenc
     seqlen = model.seqlen
     nsamples = ids.numel() // seqlen
@@ -93,34 +195,11 @@ def pp_eval(model, arch, testenc, dev, layers_dist=None, verbose=False):
     place_stage(model, arch, lo, hi, dev, first, last)
     use_cache = model.config.use_cache
     model.config.use_cache = False
-    dtype = next(iter(layers[lo].parameters())).dtype if hi > lo else torch.float16
-    shape = (1, seqlen, model.config.hidden_size)
-    bufs = [torch.empty(shape, dtype=dtype, device=dev) for _ in range(2)]
-    recv_req = [None, None]
-    send_req = []
+    batches = [ids[:, j * seqlen:(j + 1) * seqlen] for j in range(nsamples)]
     nll = torch.zeros((), dtype=torch.float32, device=dev)
-    if not first and nsamples:
-        recv_req[0] = dist.irecv(bufs[0], src=rank - 1)
-    for j in range(nsamples):
-        batch = ids[:, j * seqlen:(j + 1) * seqlen].to(dev)
-        h0, kw = evalloop.layer_inputs(model, arch, batch)
-        if first:
-            h = h0
-        else:
-            if j + 1 < nsamples:                      # post the next receive before computing this sample
-                recv_req[(j + 1) & 1] = dist.irecv(bufs[(j + 1) & 1], src=rank - 1)
-            recv_req[j & 1].wait()
-            h = bufs[j & 1].clone()
-        for i in range(lo, hi):
-            h = evalloop._call_layer(layers[i], h, kw)
-        if last:
-            nll += evalloop.sample_logits_nll(model, arch, h, batch, seqlen)
-        else:
-            send_req.append((dist.isend(h.contiguous(), dst=rank + 1), h))
-            if len(send_req) > 2:
-                send_req.pop(0)[0].wait()
-    for r, _ in send_req:
-        r.wait()
+    if nsamples:
+        stage = PipelineStage(model, arch, lo, hi, dev, batches[0], graph=graph)
+        nll = stage.run(batches)
     count = torch.tensor(float(nsamples * seqlen), device=dev)
     t = torch.stack([nll, count]) if last else torch.zeros(2, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)         # only the last stage contributes

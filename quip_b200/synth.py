@@ -108,9 +108,14 @@ def init_synthetic_(ql, seed=0, w_std=0.02):
     return ql
 
 
-def build_synthetic_model(config, device, bits=2, incoh='blocked', rescale=True, seed=0, seqlen=2048, dtype=torch.float16):
+def build_synthetic_model(config, device, bits=2, incoh='blocked', rescale=True, seed=0, seqlen=2048, dtype=torch.float16,
+                          layer_range=None, head=True):
     """A random-init HF OPT / Llama model whose decoder Linears are synthetic packed QuantLinears, created on
-    `device` without ever allocating the dense decoder weights (meta-device construction)."""
+    `device` without ever allocating the dense decoder weights (meta-device construction).
+
+    layer_range=(lo, hi): a pipeline stage -- only decoder layers lo..hi-1 are materialised (the others stay on the meta
+    device and must not be called); head=False leaves final norm / lm_head on the meta device too.  The embedding and the
+    rotary / position modules are always real: every stage derives the layer kwargs from them once."""
     import torch.nn as nn
     from .modelutils import find_layers
     from .quant import QuantLinear
@@ -129,9 +134,14 @@ def build_synthetic_model(config, device, bits=2, incoh='blocked', rescale=True,
     finally:
         torch.set_default_dtype(prev)
     layers = model.model.layers if is_llama else model.model.decoder.layers
+    lo, hi = layer_range or (0, len(layers))
     k = 0
-    for layer in layers:
-        for name, lin in find_layers(layer).items():
+    for li, layer in enumerate(layers):
+        names = find_layers(layer)
+        if not (lo <= li < hi):
+            k += len(names)                                       # same seeds per layer whatever the stage split
+            continue
+        for name, lin in names.items():
             ql = QuantLinear(bits, lin.in_features, lin.out_features, bias=lin.bias is not None, incoh=incoh,
                              rescale=rescale).to(device)
             init_synthetic_(ql, seed=seed * 100003 + k)
@@ -142,7 +152,19 @@ def build_synthetic_model(config, device, bits=2, incoh='blocked', rescale=True,
                 parent = getattr(parent, part)
             setattr(parent, leaf, ql)
     gen = torch.Generator(device=device).manual_seed(seed + 7)
+    skip = set()
+    for li, layer in enumerate(layers):
+        if not (lo <= li < hi):
+            skip.update(id(m) for m in layer.modules())
+    if not head:
+        dec = model.model if is_llama else model.model.decoder
+        for mod in (getattr(dec, 'norm', None), getattr(dec, 'final_layer_norm', None), getattr(dec, 'project_out', None),
+                    model.lm_head):
+            if mod is not None:
+                skip.update(id(m) for m in mod.modules())
     for mod in model.modules():
+        if id(mod) in skip:
+            continue
         for pname, p in list(mod._parameters.items()):
             if p is None or not p.is_meta:
                 continue
@@ -165,5 +187,20 @@ LLAMA2_7B = dict(vocab_size=32000, hidden_size=4096, intermediate_size=11008, nu
                  num_attention_heads=32, num_key_value_heads=32, max_position_embeddings=4096, rms_norm_eps=1e-5)
 OPT_1_3B = dict(vocab_size=50272, hidden_size=2048, ffn_dim=8192, num_hidden_layers=24, num_attention_heads=32,
                 max_position_embeddings=2048, word_embed_proj_dim=2048, do_layer_norm_before=True)
+OPT_30B = dict(vocab_size=50272, hidden_size=7168, ffn_dim=28672, num_hidden_layers=48, num_attention_heads=56,
+               max_position_embeddings=2048, word_embed_proj_dim=7168, do_layer_norm_before=True)
+LLAMA2_70B = dict(vocab_size=32000, hidden_size=8192, intermediate_size=28672, num_hidden_layers=80,
+                  num_attention_heads=64, num_key_value_heads=8, max_position_embeddings=4096, rms_norm_eps=1e-5)
 OPT_125M = dict(vocab_size=50272, hidden_size=768, ffn_dim=3072, num_hidden_layers=12, num_attention_heads=12,
                 max_position_embeddings=2048, word_embed_proj_dim=768, do_layer_norm_before=True)
+
+
+MODELS = {'llama7b': ('llama', LLAMA2_7B), 'llama70b': ('llama', LLAMA2_70B), 'opt125m': ('opt', OPT_125M),
+          'opt1.3b': ('opt', OPT_1_3B), 'opt30b': ('opt', OPT_30B)}
+
+
+def model_config(name, **overrides):
+    """HF config of one of the BASELINE.json model shapes (SURVEY section 8 header)."""
+    from transformers import LlamaConfig, OPTConfig
+    family, kw = MODELS[name]
+    return (LlamaConfig if family == 'llama' else OPTConfig)(**{**kw, **overrides})

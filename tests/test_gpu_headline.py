@@ -128,3 +128,24 @@ def test_golden_4096_layer_from_the_live_reference():
     err = rel_err(ql(xr), torch.nn.functional.linear(xr, W_ref))
     _report('golden_big_4096', M=2048, fresh_inputs=True, rel_err_vs_reference=err)
     assert err < 1e-3, err
+
+
+@pytest.mark.parametrize('K,N', [(8192, 8192), (8192, 1024), (8192, 28672), (28672, 8192), (7168, 7168), (7168, 28672),
+                                 (28672, 7168), (2048, 2048), (2048, 8192), (8192, 2048)])
+def test_other_model_shapes_at_2048_tokens(K, N):
+    """Layer shapes of BASELINE configs[1], [3], [4] (OPT-1.3b, OPT-30b, Llama-2-70B: sides 2048 = 64 x 32, 7168 = 224 x 32,
+    8192 = 128 x 64, 28672 = 448 x 64, 1024 = 32 x 32) through the many-token route -- dense tcgen05 passes for the wide
+    blocks, small-block passes, the one-kernel side where both blocks are 32 / 64 wide -- against the fp32 restatement."""
+    from quip_b200 import quant as Q
+    from quip_b200.selfcheck import rel_err, restated_forward
+    from quip_b200.synth import synth_layer_parts
+    tp = synth_layer_parts(K=K, N=N, bits=2, incoh='blocked', rescale=True, bias=(K in (7168, 2048) or N in (7168, 2048)), seed=K + N)
+    ql = Q.QuantLinear(infeatures=K, outfeatures=N, **Q.spec_from_parts(tp))
+    ql.pack_parts(tp)
+    ql = ql.cuda()
+    x = _inputs(2048, K, K + N)
+    for M in (2048, 333):
+        y = ql(x[:M])
+        err = rel_err(y, restated_forward(ql, x[:M]))
+        _report('quantlinear_other_shapes', K=K, N=N, M=M, rel_err_vs_restatement=err)
+        assert err < 1e-3, (K, N, M, err)

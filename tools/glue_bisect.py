@@ -86,6 +86,9 @@ def main():
             hf_final = r.clone()
             hf_sd = list(sd_calls)
             sd_calls.clear()
+            for hk in hooks:                                # the fused stack calls the same linear modules: stop recording
+                hk.remove()
+            hooks.clear()
             trace = []
             fu_final = fused.llama_stack(layers, h0.clone(), kw, trace=trace)
             fu_sd = list(sd_calls)
