@@ -130,6 +130,15 @@ int quip_rope(void* q, void* k, const void* cos, const void* sin, int64_t rows, 
               int32_t n_kv_heads, int32_t head_dim, void* stream);
 int quip_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream);
 
+/* Signature-compatible replacement of the reference's own native call (quant_cuda.vecquant3matmul quant.py:229-230,
+ * vecquant4matmul zeroShot/models/quant.py:207-208): ONE token, fp32, on the REFERENCE's packed layout
+ * (bits 3: int32 (K*3/32, N) as Quant3Linear.pack writes it; bits 4: (K/8, N); bits 2: (K/16, N)):
+ *     mul[n] += sum_k (scales[n] * code[k][n] - zeros[n]) * vec[k]        (in-place accumulate, like the reference's call)
+ * so a checkpoint packed by the reference runs without conversion.  K % 32 == 0.  quip_qlinear_forward on the native
+ * layout is the fast path; this one is a plain HBM-streaming kernel. */
+int quip_vecquant_matmul(const float* vec, const int32_t* mat, float* mul, const float* scales, const float* zeros,
+                         int32_t K, int32_t N, int32_t bits, void* stream);
+
 /* codes (N,K) uint8 row-major <-> native packed layout.  Replaces Quant3Linear.pack (quant.py:185-220). */
 int quip_pack_codes(const uint8_t* codes_nk, int32_t N, int32_t K, int32_t bits, int32_t* qweight,
                     void* stream);
@@ -140,6 +149,27 @@ int quip_unpack_codes(const int32_t* qweight, int32_t N, int32_t K, int32_t bits
 int quip_convert_ref(const int32_t* ref_qweight, int32_t K, int32_t N, int32_t bits,
                      uint8_t* codes_nk, void* stream);
 size_t quip_packed_words(int32_t N, int32_t K, int32_t bits);
+
+/* Quantisation-time hot loop: the column-sequential part of LDLQ rounding for one block of
+ * <= 128 columns, all rows in one launch (reference: the Python column loops of round_ldl / round_ldl_block,
+ * vector_balance.py:155-199, :218-257).  All matrices fp32, column-major over rows ("transposed": element (row r,
+ * column j) at [j*ld + r]); the feedback of the finished blocks is the caller's GEMM (quip_b200/quantize.py).
+ *   quip_ldlq_block    q[:, j] = clamp(floor(base[:, j] + sum_{j' > j} err[:, j'] * Lb[j'][j] + 1/2), 0, 2^bits - 1),
+ *                      err[:, j] = w[:, j] - q[:, j], for j = cnt-1 .. 0.  base = w[:, blk] + err[:, done] @ L[done, blk];
+ *                      Lb (cnt, cnt) row-major = L[blk, blk] - I (unit-lower LDL factor of H, strictly lower part read).
+ *   quip_greedy_block  one coordinate-descent sweep over the block (vector_balance.py:267-283): for i = cnt-1 .. 0,
+ *                      move = wr_i - rint(wr_i - (pre_i + sum_j s_j Hb[j][i]) / Hb[i][i]); wr_i -= move; s_i -= move.
+ *                      pre = s[:, outside blk] @ Hn[outside, blk]; Hb = Hn[blk, blk]; wr, s updated in place. */
+int quip_ldlq_block(const float* baseT, const float* wT, const float* Lb, float* qT, float* errT, int64_t m, int64_t ld,
+                    int32_t cnt, int32_t bits, void* stream);
+int quip_greedy_block(const float* preT, const float* Hb, float* wrT, float* sT, int64_t m, int64_t ld, int32_t cnt,
+                      void* stream);
+
+/* Calibration Hessian (reference QuantMethod.add_batch, method.py:98-120): H += X^T X for
+ * X (tokens, K) fp16 row-major, H (K, K) float64 row-major.  Products on the fp16 tensor cores (exact in float32), float32
+ * sums over 256 tokens, float64 carry in H.  Only the upper BLOCK triangle of 128 x 128 tiles is updated (tile row <= tile
+ * column, diagonal tiles whole): mirror it once after the last batch.  K % 8 == 0. */
+int quip_hessian_accumulate(const void* x, double* H, int64_t tokens, int32_t K, void* stream);
 
 /* Optional per-launch timing of the contraction kernels with CUDA events recorded on the launch stream
  * (bench.py's roofline leg).  path: 1 = mma.sync skinny kernel, 2 = tcgen05 kernel.  quip_timing_read
@@ -152,8 +182,7 @@ int quip_timing_read(int path, double* total_ms, int64_t* launches, double* flop
 /* Routing switches for ablations, tests and micro-benchmarks (defaults in parentheses); results do not depend on them.
  *   "side_fused" (1)  M > 8: a whole incoherence side in one kernel when both blocks are 32/64 wide and factors_frag is set
  *   "fewtok" (1)      M <= 8: few-token pass / gather kernels (fused input gather, output scatter + bias)
- *   "fewtok_max_m" (8)  8..32: token count up to which the few-token passes run (batched decode; > 8 staged, not yet
- *                     measured on a GPU)
+ *   "fewtok_max_m" (32) 8..32: token count up to which the few-token passes run (batched decode)
  *   "pdl" (1)         programmatic dependent launch along the few-token chain
  *   "gemv" (1)        M <= 8: whole-K qgemv kernels (0: split-K mma.sync kernel)
  *   "gv_int" (1)      qgemv: int8 tensor-core path for 2-/4-bit and <= 5 tokens (0: fp16 path)

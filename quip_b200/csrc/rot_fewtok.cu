@@ -231,7 +231,8 @@ gather_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, in
 
 int launch_pdl(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args);   // api.cu
 
-int g_fewtok_max_m = 8;       // quip_config("fewtok_max_m", 32): batched decode (9..32 tokens) through the few-token kernels
+int g_fewtok_max_m = 32;      // 9..32 tokens (batched decode) through the few-token kernels too; quip_config("fewtok_max_m", 8)
+                              // sends them to the many-token route instead
 
 bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n) {
   return M <= g_fewtok_max_m && M <= 32 && ps->p % 16 == 0 && ps->p >= 16 && (n % 8 == 0) && (((uintptr_t)ps->factors) & 15) == 0;

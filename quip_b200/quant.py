@@ -595,6 +595,71 @@ class QuantLinear(nn.Module):
                 f'incoh={self.incoh}, rescale={self.rescale}')
 
 
+
+# ----------------------------------------------------------------------------------------------
+# the reference's own packed modules, running on the replacement of its absent quant_cuda extension
+# ----------------------------------------------------------------------------------------------
+def _vecquant(vec, mat, mul, scales, zeros, bits):
+    if not (vec.is_cuda and mat.is_cuda and mul.is_cuda):
+        raise RuntimeError('vecquant matmul runs on a CUDA device only (there is no CPU fallback)')
+    K = vec.numel()
+    N = mul.numel()
+    if mat.dtype != torch.int32 or tuple(mat.shape) != (K * bits // 32, N):
+        raise ValueError(f'packed matrix must be int32 ({K * bits // 32}, {N}), got {mat.dtype} {tuple(mat.shape)}')
+    if vec.dtype != torch.float32 or mul.dtype != torch.float32 or not mul.is_contiguous():
+        raise ValueError('vec and mul must be fp32 (mul contiguous: it is accumulated in place)')
+    sc, ze = scales.reshape(-1).float().contiguous(), zeros.reshape(-1).float().contiguous()
+    lib = _lib.load()
+    with torch.cuda.device(vec.device):
+        _lib.check(lib.quip_vecquant_matmul(_lib.ptr(vec.contiguous()), _lib.ptr(mat.contiguous()), _lib.ptr(mul), _lib.ptr(sc),
+                                            _lib.ptr(ze), K, N, bits, C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+
+def vecquant3matmul(vec, mat, mul, scales, zeros):
+    """quant_cuda.vecquant3matmul (quant.py:229-230): mul += (scales*code - zeros) . vec on the reference's 3-bit layout."""
+    _vecquant(vec, mat, mul, scales, zeros, 3)
+
+
+def vecquant4matmul(vec, mat, mul, scales, zeros):
+    """quant_cuda.vecquant4matmul (zeroShot/models/quant.py:207-208), the 4-bit layout of Quant4Linear."""
+    _vecquant(vec, mat, mul, scales, zeros, 4)
+
+
+class Quant3Linear(nn.Module):
+    """The reference's Quant3Linear (quant.py:173-233) with the same buffers, layout and single-token contract -- a
+    state_dict written from the reference's module loads unchanged -- on quip_vecquant_matmul instead of quant_cuda.
+    `to_native()` converts it into the QuantLinear of this package (any token count, tensor cores)."""
+    BITS = 3
+
+    def __init__(self, infeatures, outfeatures):
+        super().__init__()
+        self.infeatures, self.outfeatures = infeatures, outfeatures
+        self.register_buffer('zeros', torch.zeros((outfeatures, 1)))
+        self.register_buffer('scales', torch.zeros((outfeatures, 1)))
+        self.register_buffer('bias', torch.zeros(outfeatures))
+        self.register_buffer('qweight', torch.zeros((infeatures * self.BITS // 32, outfeatures), dtype=torch.int32))
+
+    def forward(self, x):
+        if x.shape[-1] == x.numel():                                  # quant.py:223: one token only
+            outshape = list(x.shape)
+            y = self.bias.float().clone()
+            outshape[-1] = self.bias.numel()
+            _vecquant(x.reshape(-1).float(), self.qweight, y, self.scales, self.zeros, self.BITS)
+            return y.to(x.dtype).reshape(outshape)
+        raise ValueError('Only supports a single token currently.')
+
+    def to_native(self):
+        q = QuantLinear(self.BITS, self.infeatures, self.outfeatures, bias=True).to(self.qweight.device)
+        codes = convert_ref_qweight(self.qweight, self.infeatures, self.outfeatures, self.BITS)
+        q._install(codes, self.scales.float().reshape(-1, 1), self.zeros.float().reshape(-1, 1), self.bias)
+        return q
+
+
+class Quant4Linear(Quant3Linear):
+    """zeroShot/models/quant.py:185-212 (buffers and forward; construct empty and load_state_dict, or pack with
+    quip_b200.quant.make_quant4 for the native module)."""
+    BITS = 4
+
 def spec_from_parts(parts: LayerParts):
     """Constructor keyword arguments of the QuantLinear that can hold `parts`."""
     incoh = None

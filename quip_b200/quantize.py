@@ -23,20 +23,45 @@ from .capture import Butterfly, LayerParts, affine_from_quantizer, butterfly_fac
 # calibration
 # ----------------------------------------------------------------------------------------------------------------
 class HessianAccumulator:
-    """H = sum_b X_b^T X_b / #batches, float64 accumulation (method.py:98-123; the count is of batches, not tokens)."""
+    """H = sum_b X_b^T X_b / #batches, float64 accumulation (method.py:98-123; the count is of batches, not tokens).
+
+    On a CUDA device fp16 activations go through quip_hessian_accumulate (csrc/hessian.cu): tensor-core products -- exact in
+    float32 for fp16 inputs -- summed in float32 over 256 tokens and carried in the float64 H, instead of the reference's
+    float64 GEMM per batch.  Other dtypes / the CPU use the float64 matmul."""
 
     def __init__(self, features, device='cpu'):
         self.H = torch.zeros((features, features), dtype=torch.float64, device=device)
         self.batches = 0
+        self._upper_only = False                            # the kernel fills the upper block triangle only
 
     @torch.no_grad()
     def add_batch(self, x):
         x = x if x.dim() == 3 else x.unsqueeze(0)
         self.batches += x.shape[0]
-        flat = x.reshape(-1, x.shape[-1]).to(self.H.device, torch.float64)
+        flat = x.reshape(-1, x.shape[-1])
+        K = flat.shape[1]
+        if self.H.is_cuda and flat.dtype == torch.float16 and K % 8 == 0:
+            import ctypes as C
+            from . import _lib
+            flat = flat.to(self.H.device).contiguous()
+            with torch.cuda.device(self.H.device):
+                _lib.check(_lib.load().quip_hessian_accumulate(_lib.ptr(flat), _lib.ptr(self.H), flat.shape[0], K,
+                                                               C.c_void_p(torch.cuda.current_stream(self.H.device).cuda_stream)))
+            self._upper_only = True
+            return
+        if self._upper_only:
+            self._mirror()
+        flat = flat.to(self.H.device, torch.float64)
         self.H.addmm_(flat.T, flat)
 
+    def _mirror(self):
+        up = torch.triu(self.H)
+        self.H = up + torch.triu(self.H, 1).T
+        self._upper_only = False
+
     def result(self):
+        if self._upper_only:
+            self._mirror()
         return (self.H / max(self.batches, 1)).to(torch.float32)
 
 
@@ -99,10 +124,64 @@ def butterfly_apply_t(bf, x):
 # rounding
 # ----------------------------------------------------------------------------------------------------------------
 @torch.no_grad()
-def ldlq_round(w, H, nbits, greedy_passes=0, block=128):
+def ldlq_round_cuda(w, H, nbits, greedy_passes=0, block=128):
+    """ldlq_round on a CUDA device with the column-sequential part in hand-written kernels (csrc/ldlq.cu through the C ABI:
+    quip_ldlq_block / quip_greedy_block).  Per block of 128 columns: one fp32 GEMM for the feedback of the finished blocks
+    (torch / cuBLAS, TF32 off) and ONE kernel launch that walks the block's columns for all rows -- instead of the
+    reference's d GEMV launches per pass (vector_balance.py:179-183, :186-196)."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    assert w.is_cuda and H.is_cuda and 1 <= block <= 128
+    m, d = w.shape
+    prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        H = H.float()
+        wT = w.float().T.contiguous()                            # (d, m): rows contiguous
+        Cf = torch.linalg.cholesky(H)
+        Lf = (Cf / torch.diagonal(Cf).unsqueeze(0) - torch.eye(d, dtype=H.dtype, device=H.device)).contiguous()
+        qT = torch.empty_like(wT)
+        errT = torch.zeros_like(wT)
+        st = C.c_void_p(torch.cuda.current_stream(w.device).cuda_stream)
+        with torch.cuda.device(w.device):
+            for i2 in range(d, 0, -block):
+                i1 = max(0, i2 - block)
+                baseT = wT[i1:i2] if i2 == d else torch.addmm(wT[i1:i2], Lf[i2:, i1:i2].T, errT[i2:])
+                Lb = Lf[i1:i2, i1:i2].contiguous()
+                _lib.check(lib.quip_ldlq_block(_lib.ptr(baseT.contiguous()), _lib.ptr(wT[i1:i2]), _lib.ptr(Lb), _lib.ptr(qT[i1:i2]),
+                                               _lib.ptr(errT[i1:i2]), m, m, i2 - i1, nbits, st))
+            if greedy_passes:
+                top = float(2 ** nbits - 1)
+                Hn = (H / torch.diagonal(H).max()).contiguous()
+                wrT = qT.clone()
+                sT = qT - wT                                      # s = w_hat - w
+                for _ in range(greedy_passes):
+                    for i2 in range(d, 0, -block):
+                        i1 = max(0, i2 - block)
+                        # s of every column outside the block (finished blocks of this sweep and untouched ones) times H
+                        preT = Hn[i1:i2, :i1] @ sT[:i1] + Hn[i1:i2, i2:] @ sT[i2:]
+                        Hb = Hn[i1:i2, i1:i2].contiguous()
+                        _lib.check(lib.quip_greedy_block(_lib.ptr(preT.contiguous()), _lib.ptr(Hb), _lib.ptr(wrT[i1:i2]),
+                                                         _lib.ptr(sT[i1:i2]), m, m, i2 - i1, st))
+                    wrT.clamp_(0, top)                            # s is NOT updated by the clamp (reference behaviour)
+                    if bool((qT == wrT).all()):
+                        break
+                    qT.copy_(wrT)
+                qT = wrT
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+    return qT.T.contiguous()
+
+
+@torch.no_grad()
+def ldlq_round(w, H, nbits, greedy_passes=0, block=128, kernels=None):
     """LDLQ adaptive rounding of w (m, d), already in grid units, against the proxy Hessian H (d, d): columns last to first,
     column i rounded to nearest after adding the feedback of the rounding errors of columns > i through the strictly lower
-    LDL factor (vector_balance.py:174-183).  Blocked: the errors of all finished blocks enter through one matmul."""
+    LDL factor (vector_balance.py:174-183).  Blocked: the errors of all finished blocks enter through one matmul.  On a
+    CUDA device the in-block column loop runs in the kernels of csrc/ldlq.cu (`kernels=False` keeps this torch loop)."""
+    if (w.is_cuda if kernels is None else kernels) and block <= 128:
+        return ldlq_round_cuda(w, H, nbits, greedy_passes, block)
     w = w.float()
     H = H.float()
     m, d = w.shape

@@ -186,7 +186,7 @@ def test_bench_decode_glue_check_logic(monkeypatch):
         self.k_cache, self.v_cache = self.k_cache.float(), self.v_cache.float()
 
     monkeypatch.setattr(dec.GraphDecoder, '__init__', init32)
-    ok, worst = bench.decode_glue_ok(m, torch.device('cpu'))
+    ok, worst, control = bench.decode_glue_ok(m, torch.device('cpu'))
     assert ok and worst < 1e-4
 
     class WrongGlue(TorchGlue):
@@ -194,6 +194,6 @@ def test_bench_decode_glue_check_logic(monkeypatch):
             return gate * up
 
     monkeypatch.setattr(fused, 'CudaGlue', WrongGlue)
-    ok, worst = bench.decode_glue_ok(m, torch.device('cpu'))
-    assert not ok and worst > 2e-3
+    ok, worst, control = bench.decode_glue_ok(m, torch.device('cpu'))
+    assert not ok and worst > 2e-3 and worst > 3 * control
     monkeypatch.delenv('QUIP_FUSED_LAYER', raising=False)

@@ -161,3 +161,52 @@ def test_qgemm_skinny_large_M_loops():
     codes, scales, zeros, X, bias, want = _qgemm_case(2, 256, 512, 100, False, 5)
     z, _ = run_qgemm(codes, scales, zeros, 2, X, path=1, bias=bias, symmetric=False)
     assert _rel(z, want) < 3e-4
+
+
+@pytest.mark.parametrize('bits', [2, 3, 4])
+@pytest.mark.parametrize('N,K', [(256, 1024), (4096, 4096), (200, 96), (11008, 4096)])
+def test_vecquant_matmul_on_the_reference_layout(bits, N, K):
+    """quip_vecquant_matmul (the stand-in for quant_cuda.vecquant3matmul / vecquant4matmul, quant.py:229-230): one fp32
+    token against the reference's own packed layout, accumulated in place."""
+    import ctypes as C
+    from quip_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(bits * 7 + N)
+    codes = rng.integers(0, 1 << bits, size=(N, K), dtype=np.uint8)
+    ref = {2: opk.ref_pack2, 3: opk.ref_pack3, 4: opk.ref_pack4}[bits](codes)
+    scales = (0.01 + 0.02 * rng.random(N)).astype(f32)
+    zeros = (scales * rng.integers(0, 1 << bits, size=N)).astype(f32)
+    x = rng.standard_normal(K).astype(f32)
+    y0 = rng.standard_normal(N).astype(f32)
+    want = y0.astype(np.float64) + (scales.astype(np.float64)[:, None] * codes - zeros.astype(np.float64)[:, None]) @ x.astype(np.float64)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    mat, vec, mul, sc, ze = t(ref.astype(np.int32)), t(x), t(y0), t(scales), t(zeros)
+    _lib.check(lib.quip_vecquant_matmul(_lib.ptr(vec), _lib.ptr(mat), _lib.ptr(mul), _lib.ptr(sc), _lib.ptr(ze), K, N, bits,
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert _rel(mul.cpu().numpy(), want) < 1e-5
+
+
+def test_reference_quant3linear_module_runs_and_converts():
+    """A Quant3Linear state_dict as the reference's pack() writes it (golden packing_ref.npz) loads into the same-named module
+    here, runs one token through the vecquant stand-in, and converts to the native QuantLinear with the same result."""
+    from quip_b200 import quant as Q
+    z = np.load(os.path.join(GOLDEN, 'packing_ref.npz'))
+    codes = z['codes3']
+    N, K = codes.shape
+    m = Q.Quant3Linear(K, N)
+    sd = dict(qweight=torch.from_numpy(z['qweight3']), scales=torch.from_numpy(z['scales3']),
+              zeros=torch.from_numpy(z['stored_zeros3']), bias=torch.linspace(-1, 1, N))
+    m.load_state_dict(sd)
+    m = m.cuda()
+    rng = np.random.default_rng(3)
+    x = torch.from_numpy(rng.standard_normal(K).astype(f32)).cuda()
+    W = z['scales3'].astype(np.float64) * codes - z['stored_zeros3'].astype(np.float64)
+    want = W @ x.cpu().numpy().astype(np.float64) + np.linspace(-1, 1, N)
+    y = m(x.reshape(1, 1, K))
+    assert y.shape == (1, 1, N) and _rel(y.reshape(-1).cpu().numpy(), want) < 1e-5
+    with pytest.raises(ValueError, match='single token'):
+        m(torch.zeros(2, K, device='cuda'))
+    # K = 1024 and N = 16 suit the native layout too
+    y2 = m.to_native()(x.half().reshape(1, K)).float().reshape(-1).cpu().numpy()
+    assert _rel(y2, want) < 2e-3

@@ -1,22 +1,19 @@
 #!/bin/bash
-# One GPU call: whole -m gpu suite (staged tests included), the glue bisect, short benches with either glue.
-#   gpurun --timeout 1500 -- 'bash tools/gpu_call.sh'
+# GPU call 3 of round 2: new kernels (LDLQ, Hessian, vecquant), whole suite, default bench.
 set -u
-out=gpurun_out/r2c1
+out=gpurun_out/r2c3
 mkdir -p $out
 rm -f gpurun_out/parity_report.jsonl
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $out/gpu.txt 2>&1
-QUIP_TEST_STAGED=1 timeout 900 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_staged.py > $out/tests.log 2>&1
-echo "gpu tests exit $?" | tee -a $out/summary.txt
-QUIP_TEST_STAGED=1 timeout 600 python -m pytest tests/test_gpu_staged.py -m gpu -q > $out/staged.log 2>&1
-echo "staged tests exit $?" | tee -a $out/summary.txt
-timeout 300 python tools/glue_bisect.py > $out/glue_bisect.json 2> $out/glue_bisect.err
-echo "glue bisect exit $?" | tee -a $out/summary.txt
-QUIP_FUSED_LAYER=1 timeout 420 python bench.py --steps 8 --warmup 3 --no-decode --no-cpu-baseline > $out/bench_fused.json 2> $out/bench_fused.err
-echo "bench fused exit $?" | tee -a $out/summary.txt
-timeout 420 python bench.py --steps 8 --warmup 3 --no-decode --no-cpu-baseline > $out/bench_auto.json 2> $out/bench_auto.err
-echo "bench auto exit $?" | tee -a $out/summary.txt
+timeout 600 python -m pytest tests/test_gpu_quantize.py -m gpu -q > $out/quantize.log 2>&1
+echo "quantize tests exit $?" | tee -a $out/summary.txt
+timeout 300 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k "vecquant or quant3linear" > $out/vecquant.log 2>&1
+echo "vecquant tests exit $?" | tee -a $out/summary.txt
+timeout 1200 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_quantize.py > $out/tests.log 2>&1
+echo "gpu suite exit $?" | tee -a $out/summary.txt
+timeout 900 python bench.py > $out/bench_default.json 2> $out/bench_default.err
+echo "bench default exit $?" | tee -a $out/summary.txt
 cp gpurun_out/parity_report.jsonl $out/ 2>/dev/null
-tail -15 $out/tests.log
-tail -8 $out/staged.log
-head -c 1500 $out/bench_fused.json
+tail -25 $out/quantize.log
+tail -8 $out/vecquant.log
+tail -6 $out/tests.log
+head -c 300 $out/bench_default.json; echo; tail -3 $out/bench_default.err
