@@ -46,6 +46,9 @@ bool pass_fewtok_ok(const QuipPass* ps, int64_t M, int n);   // rot_fewtok.cu
 int pass_fewtok(const QuipPass* ps, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
                 const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s);
 extern int g_gv_rbc, g_gv_persist, g_gv_int, g_gv_tma, g_gv_cw, g_gv_stream;  // qgemv.cu
+bool side_fewtok_ok(const QuipSide* sd, int n, int64_t M);   // rot_side_fewtok.cu: both passes of a side in one launch, M <= 8
+int side_fewtok(const QuipSide* sd, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
+                const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s);
 
 // tuning knobs (quip_config)
 static int g_use_tc2 = 0;        // route big-M contractions to the 2-CTA kernel
@@ -53,6 +56,7 @@ static int g_use_ts = 0;         // route 2-bit big-M contractions to the TS-mod
 static int g_side_fused = 1;     // many tokens: a whole side (gather + both passes [+ row sums]) in one kernel when the blocks allow
 static int g_pdl = 1;            // few-token kernels: programmatic dependent launch (weights prefetched under the previous kernel)
 static int g_use_gemv = 1;       // few-token contractions: whole-K qgemv kernel (0: the split-K kernel)
+static int g_side_fewtok = 1;    // <= 8 tokens: both passes of a side in ONE launch (rot_side_fewtok.cu), 3 launches per linear
 
 // Launch with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in
 // the stream drains; everything it does before griddepcontrol.wait must be independent of that predecessor.
@@ -194,6 +198,7 @@ extern "C" int quip_config(const char* key, int value) {
   if (!strcmp(key, "tc2")) { g_use_tc2 = value; return QUIP_OK; }
   if (!strcmp(key, "ts")) { g_use_ts = value; return QUIP_OK; }
   if (!strcmp(key, "side_fused")) { g_side_fused = value; return QUIP_OK; }
+  if (!strcmp(key, "side_fewtok")) { g_side_fewtok = value; return QUIP_OK; }
   if (!strcmp(key, "pdl")) { g_pdl = value; return QUIP_OK; }
   if (!strcmp(key, "fewtok")) { g_fewtok = value; return QUIP_OK; }
   if (!strcmp(key, "fewtok_max_m")) {
@@ -289,7 +294,11 @@ extern "C" int quip_qlinear_forward(const QuipLinearDesc* d, const void* x_, voi
   const int vpass = d->V.n ? d->V.npass : 0;
   const bool need_xsum = !(d->flags & QUIP_FLAG_SYMMETRIC) && M > SKINNY_MAX_M;
   bool have_xsum = false;
-  if (g_side_fused && M > g_fewtok_max_m && vpass == 2 && side_fused_ok(&d->V, K)) {
+  if (g_fewtok && g_side_fewtok && vpass == 2 && side_fewtok_ok(&d->V, K, M)) {
+    // a handful of tokens: gather + 1/s + both passes in one launch, every CTA computing the first-pass rows it consumes
+    if (int e = side_fewtok(&d->V, x, bufA, M, K, d->V.idx, d->inv_scale, nullptr, nullptr, s)) return e;
+    cur = bufA;
+  } else if (g_side_fused && M > g_fewtok_max_m && vpass == 2 && side_fused_ok(&d->V, K)) {
     // many tokens: the whole side in one kernel, 16 token rows resident in shared memory
     if (int e = side_fused(&d->V, x, bufA, M, d->V.idx, d->inv_scale, nullptr, nullptr, need_xsum ? xsum : nullptr, s)) return e;
     cur = bufA;
@@ -323,6 +332,8 @@ extern "C" int quip_qlinear_forward(const QuipLinearDesc* d, const void* x_, voi
   if (!u_on) return QUIP_OK;
 
   // ---- N side: y = passes(z)[idx] + bias ----
+  if (g_fewtok && g_side_fewtok && d->U.npass == 2 && (!d->U.idx || d->U.inv_idx) && side_fewtok_ok(&d->U, N, M))
+    return side_fewtok(&d->U, zbuf, y, M, N, nullptr, nullptr, d->U.inv_idx, (const __half*)d->bias, s);
   if (g_side_fused && M > g_fewtok_max_m && d->U.npass == 2 && side_fused_ok(&d->U, N))
     return side_fused(&d->U, zbuf, y, M, nullptr, nullptr, d->U.idx, (const __half*)d->bias, nullptr, s);
   const __half* zc = zbuf;

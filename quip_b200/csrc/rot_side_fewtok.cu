@@ -1,0 +1,257 @@
+// A whole incoherence side for a handful of tokens (decode, M <= 8) in ONE launch, without a grid-wide barrier.
+//
+// One side is two block-diagonal passes (reference mul_ortho_butterfly, method.py:46-67): the outputs of the first pass
+// are regrouped -- every block of the second pass takes exactly one output from each block of the first (the (p1, p2)
+// view is multiplied along its columns, then along its rows).  As separate kernels (rot_fewtok.cu) the regrouping is a
+// kernel boundary: 2.2 us of dependent launch latency per pass, four passes per QuantLinear, more than the time the bytes
+// take.  Here the CTA that owns a block c1 of the SECOND pass computes its own inputs: input j of block c1 is output
+// i_j of first-pass block c0_j, i.e. ONE ROW of that block's factor times the block's inputs,
+//
+//     t[j]    = sum_k F0[c0_j][i_j][k] * in[ src(pos0(c0_j, k)) ]              (p1 dot products of length p0)
+//     out[j'] = sum_j F1[c1][j'][j] * t[j]                                     (the second pass's block itself)
+//
+// No factor byte is read twice across the grid (row i_j of block c0_j belongs to block c1 alone); only the token vector
+// (n values per token) is read by every CTA, from L2.  Second-pass blocks wider than SF_ROWS rows are cut into row tiles:
+// those CTAs repeat the (small) first-pass dots of their block -- for the 688 x 688 blocks of an 11008 side that is 22 KB
+// of 16-wide rows from a 352 KB array that lives in L2.
+//
+// Every CTA stages the whole token vector (16-byte loads, fp16 in shared memory) and reads it through a 16-bit copy of the
+// gather index; its factor rows are pulled into L2 before griddepcontrol.wait, i.e. under the previous kernel.
+//
+// Arithmetic: fp16 factors and tokens, float32 products and sums in a fixed order, the intermediate t kept in float32
+// (one fp16 rounding fewer than the two-kernel route), output rounded to fp16 once (+ bias after the rounding, as the
+// stand-alone gather adds it).  Fusions: in_idx / in_scale (K side: gather + 1/s), out_inv / out_bias (N side).
+#include "common.cuh"
+
+namespace quip {
+
+namespace {
+
+constexpr int SF_THREADS = 256;
+constexpr int SF_MAXTOK = 8;
+constexpr int SF_DU = 4;             // first-pass dot products a warp lane group works on at once
+constexpr int SF_ROWS = 32;           // second-pass output rows per CTA when its blocks are wider than 64
+
+struct SidePassArg {
+  const __half* F;                    // [shared ? 1 : nblk][p][p] row-major
+  int p, nblk, strided, shared;
+};
+
+__device__ __forceinline__ int pos_of(const SidePassArg& ps, int blk, int j) { return ps.strided ? j * ps.nblk + blk : blk * ps.p + j; }
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// grid.x = work items: (group of `blocks_per_cta` second-pass blocks) x (row tile rt)
+template <int M>
+__global__ void __launch_bounds__(SF_THREADS)
+side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int n, SidePassArg P0, SidePassArg P1,
+                   const int32_t* __restrict__ in_idx, const float* __restrict__ in_scale,
+                   const int32_t* __restrict__ out_inv, const __half* __restrict__ out_bias, int rows_per_cta, int blocks_per_cta) {
+  extern __shared__ __align__(16) unsigned char sm_raw[];
+  const int p0 = P0.p, p1 = P1.p;
+  float* ts = reinterpret_cast<float*>(sm_raw);                                  // [blocks_per_cta][p1][M]: second-pass inputs
+  __half* raw = reinterpret_cast<__half*>(ts + (size_t)blocks_per_cta * p1 * M);  // [M][n]: the tokens (times 1/s), feature order
+  uint16_t* sidx = reinterpret_cast<uint16_t*>(raw + (size_t)M * n);              // [n]: feature of layout position q (n < 65536)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rtiles = (p1 + rows_per_cta - 1) / rows_per_cta;
+  const int item = blockIdx.x;
+  const int c1_first = (item / rtiles) * blocks_per_cta, rt = item % rtiles;
+  const int ndots = blocks_per_cta * p1;
+  const int nrows = min(rows_per_cta, p1 - rt * rows_per_cta);
+
+  // ---- before the previous kernel's results are needed: pull this CTA's factor rows into L2, read the index vector ----
+  {
+    const int lpr0 = (p0 * 2 + 127) / 128;                                        // cache lines per first-pass row
+    for (int l = tid; l < ndots * lpr0; l += SF_THREADS) {
+      const int d = l / lpr0, bl = d / p1, j = d - bl * p1, c1 = c1_first + bl;
+      if (c1 < P1.nblk) {
+        const int pos = pos_of(P1, c1, j);
+        const int c0 = P0.strided ? pos % P0.nblk : pos / p0, i = P0.strided ? pos / P0.nblk : pos % p0;
+        prefetch_l2(reinterpret_cast<const char*>(P0.F + ((size_t)(P0.shared ? 0 : c0) * p0 + i) * p0) + (l - d * lpr0) * 128);
+      }
+    }
+    const int lpr1 = (p1 * 2 + 127) / 128;
+    for (int l = tid; l < blocks_per_cta * nrows * lpr1; l += SF_THREADS) {
+      const int o = l / lpr1, bl = o / nrows, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
+      if (c1 < P1.nblk)
+        prefetch_l2(reinterpret_cast<const char*>(P1.F + ((size_t)(P1.shared ? 0 : c1) * p1 + r) * p1) + (l - o * lpr1) * 128);
+    }
+    if (in_idx)
+      for (int q = tid; q < n; q += SF_THREADS) sidx[q] = (uint16_t)__ldg(in_idx + q);
+  }
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ---- stage the tokens in feature order with 16-byte loads (times 1/s, rounded as the stand-alone gather rounds) ----
+  for (int c = tid; c < M * (n >> 3); c += SF_THREADS) {
+    const int m = c / (n >> 3), f0 = (c - m * (n >> 3)) * 8;
+    uint4 v = *reinterpret_cast<const uint4*>(in + (size_t)m * n + f0);
+    if (in_scale) {
+      __half* h = reinterpret_cast<__half*>(&v);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(__half2float(h[e]) * __ldg(in_scale + f0 + e));
+    }
+    *reinterpret_cast<uint4*>(raw + (size_t)m * n + f0) = v;
+  }
+  __syncthreads();
+  auto xval = [&](int m, int q) { return __half2float(raw[(size_t)m * n + (in_idx ? (int)sidx[q] : q)]); };
+
+  // ---- first pass, only the rows this CTA's second-pass blocks consume: `lpd` lanes per dot product, SF_DU dots per
+  // warp step so that their factor loads (L2 latency each) are in flight together ----
+  const int lpd = p0 >= 64 ? 32 : (p0 >= 32 ? 16 : 8);                            // p0 is a multiple of 16
+  const int dpw = 32 / lpd, sub = lane / lpd, ll = lane - sub * lpd;
+  for (int d0 = warp * dpw * SF_DU; d0 < ndots; d0 += (SF_THREADS / 32) * dpw * SF_DU) {
+    const __half* frow[SF_DU];
+    int c0s[SF_DU];
+    float acc[SF_DU][M];
+#pragma unroll
+    for (int u = 0; u < SF_DU; ++u) {
+      const int d = d0 + u * dpw + sub;
+      const int bl = d / p1, j = d - bl * p1, c1 = c1_first + bl;
+      frow[u] = nullptr;
+      c0s[u] = 0;
+#pragma unroll
+      for (int m = 0; m < M; ++m) acc[u][m] = 0.f;
+      if (d < ndots && c1 < P1.nblk) {
+        const int pos = pos_of(P1, c1, j);                                        // layout position of this input
+        const int c0 = P0.strided ? pos % P0.nblk : pos / p0, i = P0.strided ? pos / P0.nblk : pos % p0;
+        c0s[u] = c0;
+        frow[u] = P0.F + ((size_t)(P0.shared ? 0 : c0) * p0 + i) * p0;
+      }
+    }
+#pragma unroll 2
+    for (int k = 2 * ll; k < p0; k += 2 * lpd) {
+      __half2 f2[SF_DU];
+#pragma unroll
+      for (int u = 0; u < SF_DU; ++u) f2[u] = frow[u] ? *reinterpret_cast<const __half2*>(frow[u] + k) : __half2();
+#pragma unroll
+      for (int u = 0; u < SF_DU; ++u) {
+        const float f0 = __low2float(f2[u]), f1 = __high2float(f2[u]);
+        const int q0 = pos_of(P0, c0s[u], k), q1 = pos_of(P0, c0s[u], k + 1);
+#pragma unroll
+        for (int m = 0; m < M; ++m) acc[u][m] = fmaf(f1, xval(m, q1), fmaf(f0, xval(m, q0), acc[u][m]));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < SF_DU; ++u) {
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        for (int o = lpd >> 1; o; o >>= 1) acc[u][m] += __shfl_xor_sync(0xffffffffu, acc[u][m], o);
+      }
+      const int d = d0 + u * dpw + sub;
+      if (ll == 0 && d < ndots) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) ts[(size_t)d * M + m] = acc[u][m];
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- second pass: rows [rt * rows_per_cta, ...) of each of this CTA's blocks, a group of 4 lanes per output row ----
+  const int nout = blocks_per_cta * nrows;                                        // a multiple of 16: whole warps take part
+  for (int o4 = tid; o4 < nout * 4; o4 += SF_THREADS) {
+    const int o = o4 >> 2, part = o4 & 3;
+    const int bl = o / nrows, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
+    float acc[M];
+#pragma unroll
+    for (int m = 0; m < M; ++m) acc[m] = 0.f;
+    const bool live = c1 < P1.nblk;
+    if (live) {
+      const __half* frow = P1.F + ((size_t)(P1.shared ? 0 : c1) * p1 + r) * p1;
+      const float* tb = ts + (size_t)bl * p1 * M;
+#pragma unroll 4
+      for (int k = 8 * part; k < p1; k += 32) {                                   // 16-byte pieces of the row, interleaved over the 4 lanes
+        const uint4 v = *reinterpret_cast<const uint4*>(frow + k);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float f0 = __low2float(h2[e]), f1 = __high2float(h2[e]);
+#pragma unroll
+          for (int m = 0; m < M; ++m)
+            acc[m] = fmaf(f1, tb[(size_t)(k + 2 * e + 1) * M + m], fmaf(f0, tb[(size_t)(k + 2 * e) * M + m], acc[m]));
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < M; ++m) {
+      acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 1);
+      acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 2);
+    }
+    if (live && part == 0) {
+      const int pos = pos_of(P1, c1, r);
+      const int dst = out_inv ? __ldg(out_inv + pos) : pos;
+      const float bs = out_bias ? __half2float(__ldg(out_bias + dst)) : 0.f;
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        const float v = out_bias ? __half2float(__float2half_rn(acc[m])) + bs : acc[m];
+        out[(size_t)m * n + dst] = __float2half_rn(v);
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int launch_pdl(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_t s, void** args);   // api.cu
+
+constexpr size_t SF_SMEM_MAX = 224 * 1024;
+static int sf_blocks_per_cta(int p1) { return p1 <= 16 ? 4 : 1; }
+// second-pass inputs (float) + M tokens of n halves + n 16-bit positions
+static size_t side_fewtok_smem(int n, int p1, int M) {
+  return (size_t)sf_blocks_per_cta(p1) * p1 * M * sizeof(float) + (size_t)M * n * sizeof(__half) + (size_t)n * sizeof(uint16_t) + 16;
+}
+
+// Can this side run as one few-token kernel?  Two passes whose blocks tile each other (p0 * nblk0 == p1 * nblk1 == n,
+// one strided and one contiguous, nblk0 == p1), rows 16-byte aligned.
+bool side_fewtok_ok(const QuipSide* sd, int n, int64_t M) {
+  if (M < 1 || M > SF_MAXTOK || sd->n != n || sd->npass != 2) return false;
+  const QuipPass& a = sd->pass[0];
+  const QuipPass& b = sd->pass[1];
+  if (a.strided == b.strided) return false;
+  if ((int64_t)a.p * a.nblk != n || (int64_t)b.p * b.nblk != n || a.nblk != b.p || b.nblk != a.p) return false;
+  if (a.p % 16 || b.p % 16) return false;
+  if ((((uintptr_t)a.factors) | ((uintptr_t)b.factors)) & 15) return false;
+  if (n >= 65536 || n % 8) return false;                       // 16-bit positions in shared memory, 16-byte token loads
+  return side_fewtok_smem(n, b.p, (int)M) <= SF_SMEM_MAX;
+}
+
+int side_fewtok(const QuipSide* sd, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
+                const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s) {
+  const QuipPass& a = sd->pass[0];
+  const QuipPass& b = sd->pass[1];
+  SidePassArg P0{(const __half*)a.factors, a.p, a.nblk, a.strided, a.shared};
+  SidePassArg P1{(const __half*)b.factors, b.p, b.nblk, b.strided, b.shared};
+  // second-pass blocks up to 64 wide: whole blocks per CTA (four 16-wide ones together); wider: row tiles
+  int blocks_per_cta = sf_blocks_per_cta(b.p);
+  int rows_per_cta = b.p <= 64 ? b.p : (b.p > 512 ? SF_ROWS : 64);
+  const int rtiles = ceil_div(b.p, rows_per_cta);
+  const int items = ceil_div(b.nblk, blocks_per_cta) * rtiles;
+  const size_t smem = side_fewtok_smem(n, b.p, (int)M);
+  const void* kern = nullptr;
+  switch ((int)M) {
+    case 1: kern = (const void*)side_fewtok_kernel<1>; break;
+    case 2: kern = (const void*)side_fewtok_kernel<2>; break;
+    case 3: kern = (const void*)side_fewtok_kernel<3>; break;
+    case 4: kern = (const void*)side_fewtok_kernel<4>; break;
+    case 5: kern = (const void*)side_fewtok_kernel<5>; break;
+    case 6: kern = (const void*)side_fewtok_kernel<6>; break;
+    case 7: kern = (const void*)side_fewtok_kernel<7>; break;
+    default: kern = (const void*)side_fewtok_kernel<8>; break;
+  }
+  if (smem > 48 * 1024) {
+    static bool done[64][SF_MAXTOK + 1] = {};
+    int dev = 0;
+    QUIP_CUDA(cudaGetDevice(&dev));
+    if (!done[dev & 63][M]) {
+      QUIP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SF_SMEM_MAX));
+      done[dev & 63][M] = true;
+    }
+  }
+  void* args[] = {(void*)&in, (void*)&out, (void*)&n, (void*)&P0, (void*)&P1, (void*)&in_idx, (void*)&in_scale,
+                  (void*)&out_inv, (void*)&out_bias, (void*)&rows_per_cta, (void*)&blocks_per_cta};
+  if (int e = launch_pdl(kern, dim3((unsigned)items), dim3(SF_THREADS), smem, s, args)) return e;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return QUIP_OK;
+}
+
+}  // namespace quip

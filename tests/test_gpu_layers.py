@@ -98,7 +98,7 @@ def plan_order(tp):
 
 @pytest.mark.parametrize('K,N,incoh,bias', [(4096, 4096, 'blocked', False), (2048, 768, 'blocked', True),
                                              (768, 2048, 'blocked', False), (4096, 2048, 'kron', True)])
-@pytest.mark.parametrize('M', [9, 37, 300, 2048])
+@pytest.mark.parametrize('M', [33, 37, 300, 2048])              # <= 32 tokens take the few-token kernels
 def test_fused_side_kernel_equals_the_separate_kernels(K, N, incoh, bias, M):
     """One-kernel incoherence sides (gather + strided pass + contiguous pass [+ row sums], 16 token rows resident in
     shared memory) against the same steps as separate launches: same fp16 rounding points, so the outputs agree to
@@ -176,3 +176,41 @@ def test_sibling_group_overlap_is_bit_identical():
                 assert torch.equal(a, b)
     grp.dissolve()
     assert torch.equal(mods[0](xs[0]), serial[0][0])
+
+
+@pytest.mark.parametrize('K,N,bits,incoh,bias', [(4096, 4096, 2, 'blocked', False), (4096, 11008, 2, 'blocked', False),
+                                                 (11008, 4096, 2, 'blocked', True), (8192, 1024, 2, 'blocked', False),
+                                                 (28672, 8192, 2, 'blocked', False), (7168, 7168, 4, 'blocked', True),
+                                                 (4096, 4096, 3, 'kron', False), (2048, 8192, 4, 'noperm', True),
+                                                 (768, 3072, 2, 'blocked', True)])
+def test_one_launch_sides_for_a_handful_of_tokens(K, N, bits, incoh, bias):
+    """quip_config('side_fewtok'): for <= 8 tokens a whole incoherence side (gather, 1/s, both passes, scatter + bias) is one
+    launch in which every CTA computes the first-pass rows its second-pass block consumes (rot_side_fewtok.cu) -- three
+    launches per QuantLinear instead of five.  Same result as the two-pass route up to the rounding of the intermediate
+    (kept in float32 here), and within the layer tolerance of the fp32 restatement."""
+    from gpu_util import torch_reference_forward
+    from quip_b200 import _lib, quant as Q
+    from quip_b200.synth import synth_layer_parts
+    lib = _lib.load()
+    tp = synth_layer_parts(K=K, N=N, bits=bits, incoh=incoh, rescale=True, bias=bias, seed=K + N + bits, qfn='a')
+    ql = Q.QuantLinear(infeatures=K, outfeatures=N, **Q.spec_from_parts(tp)).cuda()
+    ql.pack_parts(tp)
+    x = (torch.randn(8, K, device='cuda') * (1 + 3 * torch.rand(K, device='cuda'))).half()
+    want = torch_reference_forward(ql, x)
+    try:
+        for M in (1, 2, 3, 5, 8):
+            lib.quip_config(b'side_fewtok', 0)
+            y0 = ql(x[:M]).float()
+            lib.quip_config(b'side_fewtok', 1)
+            before = lib.quip_launch_count()
+            y1 = ql(x[:M]).float()
+            launches = lib.quip_launch_count() - before
+            assert float((y1 - want[:M]).norm() / want[:M].norm()) < 1e-3, (M, 'vs fp32 restatement')
+            assert float((y1 - y0).norm() / y0.norm()) < 6e-4, (M, 'vs the two-pass route')
+            assert torch.equal(y1, ql(x[:M]).float())
+            if (2 * M + 2) * max(K, N) < 200 * 1024:              # the token vectors of both sides fit shared memory
+                assert launches == 3, (M, launches)
+            else:
+                assert launches <= 5, (M, launches)
+    finally:
+        lib.quip_config(b'side_fewtok', 1)

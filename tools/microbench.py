@@ -258,13 +258,15 @@ def main():
     if 'decode' in what:
         # one token through the three Llama-2-7B QuantLinear shapes, blocked butterflies + rescale (the as-run default)
         lib = _lib.load()
-        for pdl in (1, 0):
+        for (sf, pdl) in ((1, 1), (0, 1), (1, 0)):        # one-launch sides (rot_side_fewtok.cu) / two passes per side / no PDL
             lib.quip_config(b'pdl', pdl)
+            lib.quip_config(b'side_fewtok', sf)
             for (N, K) in shapes:
-                for M in (1, 4):
-                    r = bench_layer(N, K, M, 2, 'blocked', peaks, copies=4); r['pdl'] = pdl
+                for M in (1, 4, 8):
+                    r = bench_layer(N, K, M, 2, 'blocked', peaks, copies=4); r['pdl'] = pdl; r['side_fewtok'] = sf
                     res.append(r); print(r, flush=True)
         lib.quip_config(b'pdl', 1)
+        lib.quip_config(b'side_fewtok', 1)
     if 'side' in what:
         lib = _lib.load()
         for sf in (0, 1):
@@ -281,7 +283,7 @@ def main():
                 for M in (8, 16, 32):
                     r = bench_layer(N, K, M, 2, 'blocked', peaks, copies=4); r['fewtok_max_m'] = lim
                     res.append(r); print(r, flush=True)
-        lib.quip_config(b'fewtok_max_m', 8)
+        lib.quip_config(b'fewtok_max_m', 32)
     if 'glue' in what:
         # glue kernels of csrc/glue.cu against the torch launches they replace, Llama-2-7B sizes at 2048 tokens
         from transformers.models.llama import modeling_llama as ML
