@@ -1,8 +1,8 @@
 """LDLQ / LDLQ-RG adaptive rounding on the CPU (oracle; test infrastructure only, see oracle/__init__.py).
 
 SURVEY section 8(f) rank 1: the quantisation-time hot loop the reference runs as d sequential column updates in
-Python (vector_balance.py:160-212 `round_ldl`, :218-257 the blocked variant, :146-158 / :129-143 the sorted
-"RG" wrappers, :426-466 the dispatch).  This file restates the algorithm so that a GPU implementation (next on the
+Python (vector_balance.py:155-199 `round_ldl`, :218-291 the blocked variant, :139-152 / :202-215 the sorted
+"RG" wrappers, :500-530 the dispatch in quantize_weight_vecbal).  This file restates the algorithm so that a GPU implementation (next on the
 list in DESIGN.md) has a bit-exact checker for its integer codes:
 
   * L = strictly lower part of the unit-diagonal Cholesky factor of H (vector_balance.py:174-176);
@@ -11,7 +11,7 @@ list in DESIGN.md) has a bit-exact checker for its integer codes:
   * optional greedy coordinate passes on H / max(diag H) (vector_balance.py:185-202): a column moves to
     round(wr_i - (s @ H[:, i]) / H_ii) with s = wr - w kept incrementally; the clamp at the end of a pass does
     NOT update s (reference behaviour, kept);
-  * "RG" = the same on columns sorted by ascending diag(H) (vector_balance.py:129-143).
+  * "RG" = the same on columns sorted by ascending diag(H) (vector_balance.py:139-152).
 
 torch (CPU, float32) is used rather than numpy so that every rounding decision reproduces the reference's own
 float32 arithmetic; the golden codes under tests/golden/ldlq.npz come from the live reference (oracle/gen_golden_ldlq.py).

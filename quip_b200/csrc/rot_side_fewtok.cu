@@ -15,8 +15,11 @@
 // those CTAs repeat the (small) first-pass dots of their block -- for the 688 x 688 blocks of an 11008 side that is 22 KB
 // of 16-wide rows from a 352 KB array that lives in L2.
 //
-// Every CTA stages the whole token vector (16-byte loads, fp16 in shared memory) and reads it through a 16-bit copy of the
-// gather index; its factor rows are pulled into L2 before griddepcontrol.wait, i.e. under the previous kernel.
+// Latency, not bytes, is what a decode-time kernel pays for.  Before griddepcontrol.wait -- i.e. while the previous kernel
+// is still running -- a CTA requests every factor row it will use (cp.async into shared memory) and reads the gather
+// index; after the wait it stages the token vector (16-byte loads), regroups it into first-pass block order through a
+// 16-bit copy of the index (padded rows: conflict-free), and both passes run out of shared memory: one dependent global
+// round trip (the tokens) instead of one per pass.
 //
 // Arithmetic: fp16 factors and tokens, float32 products and sums in a fixed order, the intermediate t kept in float32
 // (one fp16 rounding fewer than the two-kernel route), output rounded to fp16 once (+ bias after the rounding, as the
@@ -29,7 +32,6 @@ namespace {
 
 constexpr int SF_THREADS = 256;
 constexpr int SF_MAXTOK = 8;
-constexpr int SF_DU = 4;             // first-pass dot products a warp lane group works on at once
 constexpr int SF_ROWS = 32;           // second-pass output rows per CTA when its blocks are wider than 64
 
 struct SidePassArg {
@@ -39,7 +41,29 @@ struct SidePassArg {
 
 __device__ __forceinline__ int pos_of(const SidePassArg& ps, int blk, int j) { return ps.strided ? j * ps.nblk + blk : blk * ps.p + j; }
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void cp_async16(void* smem, const void* g) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem)), "l"(g) : "memory");
+}
+
+// Shared-memory plan (bytes, every section 16-byte aligned); the same arithmetic on the host decides whether a side fits.
+struct SfPlan {
+  int xld;                 // padded length of one first-pass block in xs0 (p0 + 2 halves: conflict-free transposing stores)
+  size_t f0, f1, ts, xs0, tmp, sidx, total;
+};
+__host__ __device__ inline SfPlan sf_plan(int n, int p0, int nblk0, int p1, int M, int ndots, int nout) {
+  SfPlan pl;
+  pl.xld = p0 + 2;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 15) & ~(size_t)15; return o; };
+  pl.f0 = take((size_t)ndots * p0 * 2);            // the first-pass factor rows this CTA consumes
+  pl.f1 = take((size_t)nout * p1 * 2);             // its second-pass rows
+  pl.ts = take((size_t)ndots * M * 4);             // second-pass inputs, float
+  pl.xs0 = take((size_t)M * nblk0 * pl.xld * 2);   // tokens in first-pass block order
+  pl.tmp = take((size_t)M * n * 2);                // tokens as they lie in memory
+  pl.sidx = take((size_t)n * 2);                   // feature of layout position q (n < 65536)
+  pl.total = off;
+  return pl;
+}
 
 // grid.x = work items: (group of `blocks_per_cta` second-pass blocks) x (row tile rt)
 template <int M>
@@ -49,40 +73,45 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
                    const int32_t* __restrict__ out_inv, const __half* __restrict__ out_bias, int rows_per_cta, int blocks_per_cta) {
   extern __shared__ __align__(16) unsigned char sm_raw[];
   const int p0 = P0.p, p1 = P1.p;
-  float* ts = reinterpret_cast<float*>(sm_raw);                                  // [blocks_per_cta][p1][M]: second-pass inputs
-  __half* raw = reinterpret_cast<__half*>(ts + (size_t)blocks_per_cta * p1 * M);  // [M][n]: the tokens (times 1/s), feature order
-  uint16_t* sidx = reinterpret_cast<uint16_t*>(raw + (size_t)M * n);              // [n]: feature of layout position q (n < 65536)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rtiles = (p1 + rows_per_cta - 1) / rows_per_cta;
   const int item = blockIdx.x;
   const int c1_first = (item / rtiles) * blocks_per_cta, rt = item % rtiles;
   const int ndots = blocks_per_cta * p1;
   const int nrows = min(rows_per_cta, p1 - rt * rows_per_cta);
+  const int nout = blocks_per_cta * nrows;                                        // a multiple of 16
+  const SfPlan pl = sf_plan(n, p0, P0.nblk, p1, M, ndots, blocks_per_cta * rows_per_cta);
+  __half* F0s = reinterpret_cast<__half*>(sm_raw + pl.f0);                         // [ndots][p0]
+  __half* F1s = reinterpret_cast<__half*>(sm_raw + pl.f1);                         // [nout][p1]
+  float* ts = reinterpret_cast<float*>(sm_raw + pl.ts);                            // [ndots][M]
+  __half* xs0 = reinterpret_cast<__half*>(sm_raw + pl.xs0);                        // [M][nblk0][xld]
+  __half* tmp = reinterpret_cast<__half*>(sm_raw + pl.tmp);                        // [M][n]
+  uint16_t* sidx = reinterpret_cast<uint16_t*>(sm_raw + pl.sidx);                  // [n]
 
-  // ---- before the previous kernel's results are needed: pull this CTA's factor rows into L2, read the index vector ----
+  // ---- everything that does not depend on the previous kernel is requested now: this CTA's factor rows travel to
+  // shared memory (cp.async) and the gather index is read while the previous kernel drains ----
   {
-    const int lpr0 = (p0 * 2 + 127) / 128;                                        // cache lines per first-pass row
-    for (int l = tid; l < ndots * lpr0; l += SF_THREADS) {
-      const int d = l / lpr0, bl = d / p1, j = d - bl * p1, c1 = c1_first + bl;
+    const int cpr0 = p0 >> 3;                                                     // 16-byte pieces per first-pass row
+    for (int c = tid; c < ndots * cpr0; c += SF_THREADS) {
+      const int d = c / cpr0, pc = c - d * cpr0, bl = d / p1, j = d - bl * p1, c1 = c1_first + bl;
       if (c1 < P1.nblk) {
-        const int pos = pos_of(P1, c1, j);
+        const int pos = pos_of(P1, c1, j);                                        // layout position of this input
         const int c0 = P0.strided ? pos % P0.nblk : pos / p0, i = P0.strided ? pos / P0.nblk : pos % p0;
-        prefetch_l2(reinterpret_cast<const char*>(P0.F + ((size_t)(P0.shared ? 0 : c0) * p0 + i) * p0) + (l - d * lpr0) * 128);
+        cp_async16(F0s + (size_t)d * p0 + 8 * pc, P0.F + ((size_t)(P0.shared ? 0 : c0) * p0 + i) * p0 + 8 * pc);
       }
     }
-    const int lpr1 = (p1 * 2 + 127) / 128;
-    for (int l = tid; l < blocks_per_cta * nrows * lpr1; l += SF_THREADS) {
-      const int o = l / lpr1, bl = o / nrows, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
-      if (c1 < P1.nblk)
-        prefetch_l2(reinterpret_cast<const char*>(P1.F + ((size_t)(P1.shared ? 0 : c1) * p1 + r) * p1) + (l - o * lpr1) * 128);
+    const int cpr1 = p1 >> 3;
+    for (int c = tid; c < nout * cpr1; c += SF_THREADS) {
+      const int o = c / cpr1, pc = c - o * cpr1, bl = o / nrows, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
+      if (c1 < P1.nblk) cp_async16(F1s + (size_t)o * p1 + 8 * pc, P1.F + ((size_t)(P1.shared ? 0 : c1) * p1 + r) * p1 + 8 * pc);
     }
-    if (in_idx)
-      for (int q = tid; q < n; q += SF_THREADS) sidx[q] = (uint16_t)__ldg(in_idx + q);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int q = tid; q < n; q += SF_THREADS) sidx[q] = (uint16_t)(in_idx ? __ldg(in_idx + q) : q);
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
-  // ---- stage the tokens in feature order with 16-byte loads (times 1/s, rounded as the stand-alone gather rounds) ----
+  // ---- the tokens: 16-byte loads in memory order (times 1/s, rounded as the stand-alone gather rounds) ... ----
   for (int c = tid; c < M * (n >> 3); c += SF_THREADS) {
     const int m = c / (n >> 3), f0 = (c - m * (n >> 3)) * 8;
     uint4 v = *reinterpret_cast<const uint4*>(in + (size_t)m * n + f0);
@@ -91,65 +120,57 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
 #pragma unroll
       for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(__half2float(h[e]) * __ldg(in_scale + f0 + e));
     }
-    *reinterpret_cast<uint4*>(raw + (size_t)m * n + f0) = v;
+    *reinterpret_cast<uint4*>(tmp + (size_t)m * n + f0) = v;
   }
   __syncthreads();
-  auto xval = [&](int m, int q) { return __half2float(raw[(size_t)m * n + (in_idx ? (int)sidx[q] : q)]); };
+  // ---- ... then into first-pass block order: xs0[m][c0][k] = x[m][idx[pos0(c0, k)]].  The loop runs over layout
+  // positions q (index reads conflict-free); the row padding makes the transposing stores conflict-free too ----
+  for (int q = tid; q < n; q += SF_THREADS) {
+    const int c0 = P0.strided ? q % P0.nblk : q / p0, k = P0.strided ? q / P0.nblk : q % p0;
+    const int src = sidx[q];
+#pragma unroll
+    for (int m = 0; m < M; ++m) xs0[((size_t)m * P0.nblk + c0) * pl.xld + k] = tmp[(size_t)m * n + src];
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
 
-  // ---- first pass, only the rows this CTA's second-pass blocks consume: `lpd` lanes per dot product, SF_DU dots per
-  // warp step so that their factor loads (L2 latency each) are in flight together ----
+  // ---- first pass, only the rows this CTA's second-pass blocks consume: `lpd` lanes per dot product ----
   const int lpd = p0 >= 64 ? 32 : (p0 >= 32 ? 16 : 8);                            // p0 is a multiple of 16
   const int dpw = 32 / lpd, sub = lane / lpd, ll = lane - sub * lpd;
-  for (int d0 = warp * dpw * SF_DU; d0 < ndots; d0 += (SF_THREADS / 32) * dpw * SF_DU) {
-    const __half* frow[SF_DU];
-    int c0s[SF_DU];
-    float acc[SF_DU][M];
+  for (int d0 = warp * dpw; d0 < ndots; d0 += (SF_THREADS / 32) * dpw) {
+    const int d = d0 + sub;
+    const int bl = d / p1, j = d - bl * p1, c1 = c1_first + bl;
+    float acc[M];
 #pragma unroll
-    for (int u = 0; u < SF_DU; ++u) {
-      const int d = d0 + u * dpw + sub;
-      const int bl = d / p1, j = d - bl * p1, c1 = c1_first + bl;
-      frow[u] = nullptr;
-      c0s[u] = 0;
+    for (int m = 0; m < M; ++m) acc[m] = 0.f;
+    if (d < ndots && c1 < P1.nblk) {
+      const int pos = pos_of(P1, c1, j);
+      const int c0 = P0.strided ? pos % P0.nblk : pos / p0;
+      const __half* frow = F0s + (size_t)d * p0;
+      const __half* xb = xs0 + (size_t)c0 * pl.xld;
+#pragma unroll 4
+      for (int k = 2 * ll; k < p0; k += 2 * lpd) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(frow + k));
 #pragma unroll
-      for (int m = 0; m < M; ++m) acc[u][m] = 0.f;
-      if (d < ndots && c1 < P1.nblk) {
-        const int pos = pos_of(P1, c1, j);                                        // layout position of this input
-        const int c0 = P0.strided ? pos % P0.nblk : pos / p0, i = P0.strided ? pos / P0.nblk : pos % p0;
-        c0s[u] = c0;
-        frow[u] = P0.F + ((size_t)(P0.shared ? 0 : c0) * p0 + i) * p0;
-      }
-    }
-#pragma unroll 2
-    for (int k = 2 * ll; k < p0; k += 2 * lpd) {
-      __half2 f2[SF_DU];
-#pragma unroll
-      for (int u = 0; u < SF_DU; ++u) f2[u] = frow[u] ? *reinterpret_cast<const __half2*>(frow[u] + k) : __half2();
-#pragma unroll
-      for (int u = 0; u < SF_DU; ++u) {
-        const float f0 = __low2float(f2[u]), f1 = __high2float(f2[u]);
-        const int q0 = pos_of(P0, c0s[u], k), q1 = pos_of(P0, c0s[u], k + 1);
-#pragma unroll
-        for (int m = 0; m < M; ++m) acc[u][m] = fmaf(f1, xval(m, q1), fmaf(f0, xval(m, q0), acc[u][m]));
+        for (int m = 0; m < M; ++m) {
+          const float2 x = __half22float2(*reinterpret_cast<const __half2*>(xb + (size_t)m * P0.nblk * pl.xld + k));
+          acc[m] = fmaf(f.y, x.y, fmaf(f.x, x.x, acc[m]));
+        }
       }
     }
 #pragma unroll
-    for (int u = 0; u < SF_DU; ++u) {
+    for (int m = 0; m < M; ++m) {
+      for (int o = lpd >> 1; o; o >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], o);
+    }
+    if (ll == 0 && d < ndots) {
 #pragma unroll
-      for (int m = 0; m < M; ++m) {
-        for (int o = lpd >> 1; o; o >>= 1) acc[u][m] += __shfl_xor_sync(0xffffffffu, acc[u][m], o);
-      }
-      const int d = d0 + u * dpw + sub;
-      if (ll == 0 && d < ndots) {
-#pragma unroll
-        for (int m = 0; m < M; ++m) ts[(size_t)d * M + m] = acc[u][m];
-      }
+      for (int m = 0; m < M; ++m) ts[(size_t)d * M + m] = acc[m];
     }
   }
   __syncthreads();
 
   // ---- second pass: rows [rt * rows_per_cta, ...) of each of this CTA's blocks, a group of 4 lanes per output row ----
-  const int nout = blocks_per_cta * nrows;                                        // a multiple of 16: whole warps take part
-  for (int o4 = tid; o4 < nout * 4; o4 += SF_THREADS) {
+  for (int o4 = tid; o4 < nout * 4; o4 += SF_THREADS) {                           // nout * 4 is a multiple of 64: whole warps
     const int o = o4 >> 2, part = o4 & 3;
     const int bl = o / nrows, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
     float acc[M];
@@ -157,18 +178,18 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
     for (int m = 0; m < M; ++m) acc[m] = 0.f;
     const bool live = c1 < P1.nblk;
     if (live) {
-      const __half* frow = P1.F + ((size_t)(P1.shared ? 0 : c1) * p1 + r) * p1;
+      const __half* frow = F1s + (size_t)o * p1;
       const float* tb = ts + (size_t)bl * p1 * M;
-#pragma unroll 4
+#pragma unroll 2
       for (int k = 8 * part; k < p1; k += 32) {                                   // 16-byte pieces of the row, interleaved over the 4 lanes
         const uint4 v = *reinterpret_cast<const uint4*>(frow + k);
         const __half2* h2 = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float f0 = __low2float(h2[e]), f1 = __high2float(h2[e]);
+          const float2 f = __half22float2(h2[e]);
 #pragma unroll
           for (int m = 0; m < M; ++m)
-            acc[m] = fmaf(f1, tb[(size_t)(k + 2 * e + 1) * M + m], fmaf(f0, tb[(size_t)(k + 2 * e) * M + m], acc[m]));
+            acc[m] = fmaf(f.y, tb[(size_t)(k + 2 * e + 1) * M + m], fmaf(f.x, tb[(size_t)(k + 2 * e) * M + m], acc[m]));
         }
       }
     }
@@ -196,9 +217,10 @@ int launch_pdl(const void* kern, dim3 grid, dim3 block, size_t smem, cudaStream_
 
 constexpr size_t SF_SMEM_MAX = 224 * 1024;
 static int sf_blocks_per_cta(int p1) { return p1 <= 16 ? 4 : 1; }
-// second-pass inputs (float) + M tokens of n halves + n 16-bit positions
-static size_t side_fewtok_smem(int n, int p1, int M) {
-  return (size_t)sf_blocks_per_cta(p1) * p1 * M * sizeof(float) + (size_t)M * n * sizeof(__half) + (size_t)n * sizeof(uint16_t) + 16;
+static int sf_rows_per_cta(int p1) { return p1 <= 64 ? p1 : (p1 > 512 ? SF_ROWS : 64); }
+static size_t side_fewtok_smem(int n, const QuipPass& a, const QuipPass& b, int M) {
+  const int bpc = sf_blocks_per_cta(b.p);
+  return sf_plan(n, a.p, a.nblk, b.p, M, bpc * b.p, bpc * sf_rows_per_cta(b.p)).total;
 }
 
 // Can this side run as one few-token kernel?  Two passes whose blocks tile each other (p0 * nblk0 == p1 * nblk1 == n,
@@ -212,7 +234,7 @@ bool side_fewtok_ok(const QuipSide* sd, int n, int64_t M) {
   if (a.p % 16 || b.p % 16) return false;
   if ((((uintptr_t)a.factors) | ((uintptr_t)b.factors)) & 15) return false;
   if (n >= 65536 || n % 8) return false;                       // 16-bit positions in shared memory, 16-byte token loads
-  return side_fewtok_smem(n, b.p, (int)M) <= SF_SMEM_MAX;
+  return side_fewtok_smem(n, a, b, (int)M) <= SF_SMEM_MAX;
 }
 
 int side_fewtok(const QuipSide* sd, const __half* in, __half* out, int64_t M, int n, const int32_t* in_idx,
@@ -223,10 +245,10 @@ int side_fewtok(const QuipSide* sd, const __half* in, __half* out, int64_t M, in
   SidePassArg P1{(const __half*)b.factors, b.p, b.nblk, b.strided, b.shared};
   // second-pass blocks up to 64 wide: whole blocks per CTA (four 16-wide ones together); wider: row tiles
   int blocks_per_cta = sf_blocks_per_cta(b.p);
-  int rows_per_cta = b.p <= 64 ? b.p : (b.p > 512 ? SF_ROWS : 64);
+  int rows_per_cta = sf_rows_per_cta(b.p);
   const int rtiles = ceil_div(b.p, rows_per_cta);
   const int items = ceil_div(b.nblk, blocks_per_cta) * rtiles;
-  const size_t smem = side_fewtok_smem(n, b.p, (int)M);
+  const size_t smem = side_fewtok_smem(n, a, b, (int)M);
   const void* kern = nullptr;
   switch ((int)M) {
     case 1: kern = (const void*)side_fewtok_kernel<1>; break;

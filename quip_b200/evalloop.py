@@ -103,8 +103,35 @@ def layer_inputs(model, arch: Arch, batch):
     return sink['inp'], sink['kwargs']
 
 
+_NVTX = None
+
+
+def _nvtx():
+    """QUIP_NVTX=1: an NVTX range per decoder layer / stack / head (visible to ncu and nsys)."""
+    global _NVTX
+    if _NVTX is None:
+        import os
+        _NVTX = os.environ.get('QUIP_NVTX') == '1' and torch.cuda.is_available()
+    return _NVTX
+
+
+class _Range:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _nvtx():
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _nvtx():
+            torch.cuda.nvtx.range_pop()
+        return False
+
+
 def _call_layer(layer, h, kwargs):
-    out = layer(h, **kwargs)
+    with _Range('quip.decoder_layer'):
+        out = layer(h, **kwargs)
     return out[0] if isinstance(out, (tuple, list)) else out
 
 
@@ -114,7 +141,8 @@ def run_layers(model, arch: Arch, layers, h, kwargs):
     if arch.name == 'llama' and h.is_cuda:
         from . import fused
         if fused.enabled() and fused.supports(model, h, kwargs):
-            return fused.llama_stack(layers, h, kwargs)
+            with _Range('quip.fused_llama_stack'):
+                return fused.llama_stack(layers, h, kwargs)
     for layer in layers:
         h = _call_layer(layer, h, kwargs)
     return h
@@ -122,9 +150,10 @@ def run_layers(model, arch: Arch, layers, h, kwargs):
 
 def sample_logits_nll(model, arch: Arch, h, labels, seqlen):
     """final norm -> lm_head -> shifted CE on fp16 logits, scaled by seqlen (opt.py:280-295)."""
-    for mod in arch.post(model):
-        h = mod(h)
-    logits = arch.head(model)(h)
+    with _Range('quip.head_and_loss'):
+        for mod in arch.post(model):
+            h = mod(h)
+        logits = arch.head(model)(h)
     shift_logits = logits[:, :-1, :].contiguous()
     shift_labels = labels[:, 1:]
     loss = nn.CrossEntropyLoss()(shift_logits.view(-1, shift_logits.size(-1)), shift_labels.reshape(-1))

@@ -220,7 +220,7 @@ def ldlq_round(w, H, nbits, greedy_passes=0, block=128, kernels=None):
 
 @torch.no_grad()
 def ldlq_rg_round(w, H, nbits, greedy_passes=0, block=128):
-    """LDLQ-RG: the same on columns sorted by ascending diag(H) (vector_balance.py:129-143)."""
+    """LDLQ-RG: the same on columns sorted by ascending diag(H) (round_sorted_ldlqRG, vector_balance.py:139-152)."""
     p = torch.argsort(torch.diagonal(H))
     out = torch.empty_like(w, dtype=torch.float32)
     out[:, p] = ldlq_round(w[:, p], H[p][:, p], nbits, greedy_passes, block)

