@@ -32,6 +32,7 @@ namespace {
 
 constexpr int SF_THREADS = 256;
 constexpr int SF_MAXTOK = 8;
+constexpr int SF_MLP = 8;             // independent 16-byte loads a thread keeps in flight in the staging loops
 constexpr int SF_ROWS = 32;           // second-pass output rows per CTA when its blocks are wider than 64
 
 struct SidePassArg {
@@ -48,7 +49,7 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* g) {
 // Shared-memory plan (bytes, every section 16-byte aligned); the same arithmetic on the host decides whether a side fits.
 struct SfPlan {
   int xld;                 // padded length of one first-pass block in xs0 (p0 + 2 halves: conflict-free transposing stores)
-  size_t f0, f1, ts, xs0, tmp, sidx, total;
+  size_t f0, f1, ts, od, xs0, tmp, sidx, total;
 };
 __host__ __device__ inline SfPlan sf_plan(int n, int p0, int nblk0, int p1, int M, int ndots, int nout) {
   SfPlan pl;
@@ -58,6 +59,7 @@ __host__ __device__ inline SfPlan sf_plan(int n, int p0, int nblk0, int p1, int 
   pl.f0 = take((size_t)ndots * p0 * 2);            // the first-pass factor rows this CTA consumes
   pl.f1 = take((size_t)nout * p1 * 2);             // its second-pass rows
   pl.ts = take((size_t)ndots * M * 4);             // second-pass inputs, float
+  pl.od = take((size_t)nout * 8);                  // destination index and bias of every output row of this CTA
   pl.xs0 = take((size_t)M * nblk0 * pl.xld * 2);   // tokens in first-pass block order
   pl.tmp = take((size_t)M * n * 2);                // tokens as they lie in memory
   pl.sidx = take((size_t)n * 2);                   // feature of layout position q (n < 65536)
@@ -84,6 +86,8 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
   __half* F0s = reinterpret_cast<__half*>(sm_raw + pl.f0);                         // [ndots][p0]
   __half* F1s = reinterpret_cast<__half*>(sm_raw + pl.f1);                         // [nout][p1]
   float* ts = reinterpret_cast<float*>(sm_raw + pl.ts);                            // [ndots][M]
+  int* dst_s = reinterpret_cast<int*>(sm_raw + pl.od);                             // [nout]
+  float* bias_s = reinterpret_cast<float*>(dst_s + blocks_per_cta * rows_per_cta); // [nout]
   __half* xs0 = reinterpret_cast<__half*>(sm_raw + pl.xs0);                        // [M][nblk0][xld]
   __half* tmp = reinterpret_cast<__half*>(sm_raw + pl.tmp);                        // [M][n]
   uint16_t* sidx = reinterpret_cast<uint16_t*>(sm_raw + pl.sidx);                  // [n]
@@ -106,21 +110,59 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
       if (c1 < P1.nblk) cp_async16(F1s + (size_t)o * p1 + 8 * pc, P1.F + ((size_t)(P1.shared ? 0 : c1) * p1 + r) * p1 + 8 * pc);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    for (int q = tid; q < n; q += SF_THREADS) sidx[q] = (uint16_t)(in_idx ? __ldg(in_idx + q) : q);
+    for (int o = tid; o < nout; o += SF_THREADS) {                                // where the outputs go (scatter index, bias)
+      const int bl = o / nrows, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
+      int dst = 0;
+      float bs = 0.f;
+      if (c1 < P1.nblk) {
+        const int pos = pos_of(P1, c1, r);
+        dst = out_inv ? __ldg(out_inv + pos) : pos;
+        bs = out_bias ? __half2float(__ldg(out_bias + dst)) : 0.f;
+      }
+      dst_s[o] = dst;
+      bias_s[o] = bs;
+    }
+    // the index: 16-byte loads, SF_MLP of them in flight per thread (a plain loop would pay one memory latency per turn)
+    for (int base = tid; base < (n >> 2); base += SF_THREADS * SF_MLP) {
+      int4 v[SF_MLP];
+#pragma unroll
+      for (int u = 0; u < SF_MLP; ++u) {
+        const int c = base + u * SF_THREADS;
+        v[u] = make_int4(4 * c, 4 * c + 1, 4 * c + 2, 4 * c + 3);
+        if (in_idx && c < (n >> 2)) v[u] = __ldg(reinterpret_cast<const int4*>(in_idx) + c);
+      }
+#pragma unroll
+      for (int u = 0; u < SF_MLP; ++u) {
+        const int c = base + u * SF_THREADS;
+        if (c < (n >> 2)) *reinterpret_cast<uint2*>(sidx + 4 * c) = make_uint2((uint32_t)v[u].x | ((uint32_t)v[u].y << 16),
+                                                                                (uint32_t)v[u].z | ((uint32_t)v[u].w << 16));
+      }
+    }
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- the tokens: 16-byte loads in memory order (times 1/s, rounded as the stand-alone gather rounds) ... ----
-  for (int c = tid; c < M * (n >> 3); c += SF_THREADS) {
-    const int m = c / (n >> 3), f0 = (c - m * (n >> 3)) * 8;
-    uint4 v = *reinterpret_cast<const uint4*>(in + (size_t)m * n + f0);
-    if (in_scale) {
-      __half* h = reinterpret_cast<__half*>(&v);
+  for (int base = tid; base < M * (n >> 3); base += SF_THREADS * SF_MLP) {
+    uint4 v[SF_MLP];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(__half2float(h[e]) * __ldg(in_scale + f0 + e));
+    for (int u = 0; u < SF_MLP; ++u) {
+      const int c = base + u * SF_THREADS;
+      if (c < M * (n >> 3)) v[u] = *reinterpret_cast<const uint4*>(in + (size_t)c * 8);      // (m, f0) = (c / (n/8), 8 (c % (n/8)))
     }
-    *reinterpret_cast<uint4*>(tmp + (size_t)m * n + f0) = v;
+#pragma unroll
+    for (int u = 0; u < SF_MLP; ++u) {
+      const int c = base + u * SF_THREADS;
+      if (c < M * (n >> 3)) {
+        if (in_scale) {
+          const int f0 = (c % (n >> 3)) * 8;
+          __half* h = reinterpret_cast<__half*>(&v[u]);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[e] = __float2half_rn(__half2float(h[e]) * __ldg(in_scale + f0 + e));
+        }
+        *reinterpret_cast<uint4*>(tmp + (size_t)c * 8) = v[u];
+      }
+    }
   }
   __syncthreads();
   // ---- ... then into first-pass block order: xs0[m][c0][k] = x[m][idx[pos0(c0, k)]].  The loop runs over layout
@@ -199,9 +241,8 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
       acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 2);
     }
     if (live && part == 0) {
-      const int pos = pos_of(P1, c1, r);
-      const int dst = out_inv ? __ldg(out_inv + pos) : pos;
-      const float bs = out_bias ? __half2float(__ldg(out_bias + dst)) : 0.f;
+      const int dst = dst_s[o];
+      const float bs = bias_s[o];
 #pragma unroll
       for (int m = 0; m < M; ++m) {
         const float v = out_bias ? __half2float(__float2half_rn(acc[m])) + bs : acc[m];
@@ -241,6 +282,7 @@ int side_fewtok(const QuipSide* sd, const __half* in, __half* out, int64_t M, in
                 const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s) {
   const QuipPass& a = sd->pass[0];
   const QuipPass& b = sd->pass[1];
+  QUIP_CHECK_ARG((((uintptr_t)in | (uintptr_t)in_idx) & 15) == 0, "few-token side: tokens and index must be 16-byte aligned");
   SidePassArg P0{(const __half*)a.factors, a.p, a.nblk, a.strided, a.shared};
   SidePassArg P1{(const __half*)b.factors, b.p, b.nblk, b.strided, b.shared};
   // second-pass blocks up to 64 wide: whole blocks per CTA (four 16-wide ones together); wider: row tiles
