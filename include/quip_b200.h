@@ -129,6 +129,12 @@ int quip_rmsnorm(const void* x, const void* residual, const void* weight, void* 
 int quip_rope(void* q, void* k, const void* cos, const void* sin, int64_t rows, int32_t n_q_heads,
               int32_t n_kv_heads, int32_t head_dim, void* stream);
 int quip_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* stream);
+/*   quip_silu_mul_gather  the same product with the permutations of the surrounding incoherence sides folded in:
+ *                  out[r][l] = silu(gate[r][idx[l] & 0xFFFF]) * up[r][idx[l] >> 16] for rows of n < 65536 features; gate / up
+ *                  are the projections in their N-side layout order (quip_qlinear_forward with U.idx = NULL), out feeds a
+ *                  forward with V.idx = NULL: idx[l] = u_idx_gate[v_idx_down[l]] | u_idx_up[v_idx_down[l]] << 16. */
+int quip_silu_mul_gather(const void* gate, const void* up, const uint32_t* idx, void* out, int64_t rows, int32_t n,
+                         void* stream);
 
 /* Signature-compatible replacement of the reference's own native call (quant_cuda.vecquant3matmul quant.py:229-230,
  * vecquant4matmul zeroShot/models/quant.py:207-208): ONE token, fp32, on the REFERENCE's packed layout

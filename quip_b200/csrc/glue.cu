@@ -139,6 +139,49 @@ __global__ void __launch_bounds__(256) silu_mul_kernel(const __half* __restrict_
   }
 }
 
+// SiLU(gate) * up with the permutations of the three surrounding incoherence sides folded in:
+//   out[r][l] = fp16(fp16(silu(G[r][ig[l]])) * U[r][iu[l]]),   idx[l] = ig[l] | iu[l] << 16
+// G and U are the gate / up projections still in their U-side layout order (their output gathers skipped), out is the down
+// projection's input already in its V-side layout order (its input gather skipped): ig = u_idx(gate)[v_idx(down)], iu
+// likewise -- three gather kernels and silu_mul become one pass.  SG_ROWS token rows per CTA share the index loads; the rows
+// sit in shared memory (16-byte loads), the permuted reads are 2-byte shared-memory accesses, the stores 16 bytes.
+constexpr int SG_ROWS = 2;
+constexpr int SG_THREADS = 512;
+
+__global__ void __launch_bounds__(SG_THREADS)
+silu_mul_gather_kernel(const __half* __restrict__ g, const __half* __restrict__ u, const uint32_t* __restrict__ idx,
+                       __half* __restrict__ out, int64_t rows, int n) {
+  extern __shared__ __align__(16) unsigned char sg_raw[];
+  __half* gs = reinterpret_cast<__half*>(sg_raw);                 // [SG_ROWS][n]
+  __half* us = gs + (size_t)SG_ROWS * n;                          // [SG_ROWS][n]
+  const int64_t r0 = (int64_t)blockIdx.x * SG_ROWS;
+  const int nr = (int)((rows - r0) < SG_ROWS ? (rows - r0) : SG_ROWS);
+  const int nvec = n >> 3;
+  for (int c = threadIdx.x; c < nr * nvec; c += SG_THREADS) {
+    const int r = c / nvec, v = c - r * nvec;
+    reinterpret_cast<uint4*>(gs + (size_t)r * n)[v] = ldg_nc_v4(reinterpret_cast<const uint4*>(g + (r0 + r) * n) + v);
+    reinterpret_cast<uint4*>(us + (size_t)r * n)[v] = ldg_nc_v4(reinterpret_cast<const uint4*>(u + (r0 + r) * n) + v);
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < nvec; v += SG_THREADS) {
+    const uint4 i0 = __ldg(reinterpret_cast<const uint4*>(idx) + 2 * v), i1 = __ldg(reinterpret_cast<const uint4*>(idx) + 2 * v + 1);
+    const uint32_t ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
+#pragma unroll
+    for (int r = 0; r < SG_ROWS; ++r) {
+      if (r < nr) {
+        H8 o;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float gv = __half2float(gs[(size_t)r * n + (ii[e] & 0xFFFFu)]);
+          const __half sv = __float2half_rn(gv / (1.0f + expf(-gv)));
+          o.h[e] = __hmul(sv, us[(size_t)r * n + (ii[e] >> 16)]);
+        }
+        reinterpret_cast<uint4*>(out + (r0 + r) * n)[v] = o.v;
+      }
+    }
+  }
+}
+
 int stream_grid(int64_t items, int threads) {
   static int sms = 0;
   if (!sms) {
@@ -202,5 +245,27 @@ extern "C" int quip_silu_mul(const void* gate, const void* up, void* out, int64_
   silu_mul_kernel<<<stream_grid(n / 8, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)gate, (const __half*)up,
                                                                              (__half*)out, n / 8);
   QUIP_LAUNCHED("silu_mul_kernel");
+  return QUIP_OK;
+}
+
+extern "C" int quip_silu_mul_gather(const void* gate, const void* up, const uint32_t* idx, void* out, int64_t rows, int32_t n,
+                                    void* stream) {
+  QUIP_CHECK_ARG(gate && up && idx && out, "quip_silu_mul_gather: null pointer");
+  QUIP_CHECK_ARG(rows >= 0 && n > 0 && n % 8 == 0 && n < 65536, "quip_silu_mul_gather: width %d must be a multiple of 8 below 65536", n);
+  QUIP_CHECK_ARG(aligned16(gate) && aligned16(up) && aligned16(idx) && aligned16(out), "quip_silu_mul_gather: pointers must be 16-byte aligned");
+  QUIP_CHECK_ARG(gate != out && up != out, "quip_silu_mul_gather: out must not alias the inputs (it is a permutation)");
+  if (rows == 0) return QUIP_OK;
+  const size_t smem = (size_t)2 * SG_ROWS * n * sizeof(__half);
+  QUIP_CHECK_ARG(smem <= 220 * 1024, "quip_silu_mul_gather: width %d does not fit shared memory", n);
+  static size_t done[64] = {0};
+  int dev = 0;
+  QUIP_CUDA(cudaGetDevice(&dev));
+  if (smem > 48 * 1024 && smem > done[dev & 63]) {
+    QUIP_CUDA(cudaFuncSetAttribute(silu_mul_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done[dev & 63] = smem;
+  }
+  silu_mul_gather_kernel<<<(unsigned)ceil_div(rows, SG_ROWS), SG_THREADS, smem, (cudaStream_t)stream>>>(
+      (const __half*)gate, (const __half*)up, idx, (__half*)out, rows, n);
+  QUIP_LAUNCHED("silu_mul_gather_kernel");
   return QUIP_OK;
 }

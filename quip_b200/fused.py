@@ -77,6 +77,43 @@ class CudaGlue:
         return out
 
 
+    def silu_mul_gather(self, gate, up, idx):
+        """silu(gate[..., ig]) * up[..., iu] with idx = ig | iu << 16 per output feature (int32 tensor): quip_silu_mul_gather."""
+        self._check(gate, up)
+        n = gate.shape[-1]
+        out = torch.empty_like(gate)
+        with torch.cuda.device(gate.device):
+            _lib.check(_lib.load().quip_silu_mul_gather(gate.data_ptr(), up.data_ptr(), idx.data_ptr(), out.data_ptr(),
+                                                        gate.numel() // n, n, self._stream(gate)))
+        return out
+
+
+def mlp_layout_plan(mlp):
+    """The combined index of the three permutations around SiLU(gate) * up of a packed Llama MLP -- the output gathers of
+    gate_proj / up_proj (y[j] = layout[u_idx[j]]) and the input gather of down_proj (layout[l] = x[v_idx[l]]) -- so that one
+    kernel (quip_silu_mul_gather) replaces three gather launches and silu_mul: for an 11008-wide side the gather is a kernel of
+    its own (29 us at 2048 tokens each, profiles/launches_r01.json).  None when the layers are not packed, have a bias /
+    unfolded 1/s at those gathers, or are too wide for 16-bit positions.  Cached on the module."""
+    from .quant import QuantLinear
+    gate, up, down = mlp.gate_proj, mlp.up_proj, mlp.down_proj
+    if not all(isinstance(m, QuantLinear) for m in (gate, up, down)):
+        return None
+    dev = gate.qweight.device
+    cached = getattr(mlp, '_quip_layout_plan', None)
+    if cached is not None and cached[0] == dev:
+        return cached[1]
+    plan = None
+    n = gate.outfeatures
+    if (dev.type == 'cuda' and n == up.outfeatures == down.infeatures and n % 8 == 0 and n < 65536 and
+            gate.layout_variant_ok(skip_out=True) and up.layout_variant_ok(skip_out=True) and down.layout_variant_ok(skip_in=True)):
+        ar = torch.arange(n, device=dev)
+        ig, iu, idn = (i if i is not None else ar for i in (gate.gather_index('u'), up.gather_index('u'), down.gather_index('v')))
+        comb = ig[idn] | (iu[idn] << 16)                                     # int64, < 2^32
+        plan = torch.where(comb >= 2 ** 31, comb - 2 ** 32, comb).to(torch.int32).contiguous()
+    mlp._quip_layout_plan = (dev, plan)
+    return plan
+
+
 def enabled():
     """The fused stack is opt-in (QUIP_FUSED_LAYER=1) until it has been measured on a B200."""
     return os.environ.get('QUIP_FUSED_LAYER') == '1'
@@ -98,10 +135,12 @@ def supports(model, h, kwargs):
     return hd % 16 == 0 and cfg.hidden_size % 8 == 0 and cfg.intermediate_size % 8 == 0
 
 
-def llama_stack(layers, h, kwargs, ops=None, trace=None):
+def llama_stack(layers, h, kwargs, ops=None, trace=None, fold_gathers=None):
     """`for layer in layers: h = layer(h, **kwargs)` for LlamaDecoderLayers on one sample h (1, S, hidden).  `trace`: an optional
     list that receives (layer index, stage name, tensor) for tools/glue_bisect.py."""
     ops = ops or CudaGlue()
+    if fold_gathers is None:
+        fold_gathers = trace is None and os.environ.get('QUIP_FOLD_GATHERS', '1') == '1'
     cos, sin = kwargs['position_embeddings']
     cos, sin = cos[0].contiguous(), sin[0].contiguous()                     # (S, head_dim)
     mask = kwargs.get('attention_mask')
@@ -151,11 +190,19 @@ def llama_stack(layers, h, kwargs, ops=None, trace=None):
         h, x = ops.rmsnorm(h, n2.weight, n2.variance_epsilon, residual=ao)
         rec(li, 'h_mid', h)
         rec(li, 'x_mlp', x)
-        g, u = mlp.gate_proj(x), mlp.up_proj(x)
-        rec(li, 'gate', g)
-        rec(li, 'up', u)
-        act = ops.silu_mul(g, u)
-        rec(li, 'act', act)
-        pend = mlp.down_proj(act)
+        plan = mlp_layout_plan(mlp) if (fold_gathers and hasattr(ops, 'silu_mul_gather')) else None
+        if plan is not None:
+            # gate / up stay in their N-side layout order, the product lands in down_proj's K-side layout order: one kernel
+            # instead of three gathers + silu_mul (same arithmetic per element, only the data movement differs)
+            g, u = mlp.gate_proj.forward_layout(x, skip_out=True), mlp.up_proj.forward_layout(x, skip_out=True)
+            act = ops.silu_mul_gather(g, u, plan)
+            pend = mlp.down_proj.forward_layout(act, skip_in=True)
+        else:
+            g, u = mlp.gate_proj(x), mlp.up_proj(x)
+            rec(li, 'gate', g)
+            rec(li, 'up', u)
+            act = ops.silu_mul(g, u)
+            rec(li, 'act', act)
+            pend = mlp.down_proj(act)
         rec(li, 'down', pend)
     return h if pend is None else h + pend

@@ -293,10 +293,10 @@ class SiblingGroup:
         self._x, self._key = None, None
         self._outs = [None] * len(self.members)
 
-    def get(self, index, x):
+    def get(self, index, x, variant=None):
         # the pending input is held by a strong reference and compared by identity: its id / address cannot be reused by a
         # different tensor while sibling outputs are pending
-        key = (x.data_ptr(), tuple(x.shape), x._version)
+        key = (x.data_ptr(), tuple(x.shape), x._version, variant)
         if x is not self._x or key != self._key or self._outs[index] is None:
             self._outs = [None] * len(self.members)         # outputs of an abandoned input are dropped
             self._x = x
@@ -312,13 +312,13 @@ class SiblingGroup:
             order = [index] + [j for j in range(len(self.members)) if j != index]
             for slot, j in enumerate(order):
                 if slot == 0:
-                    self._outs[j] = self.members[j]._forward_impl(x)
+                    self._outs[j] = self.members[j]._forward_impl(x, variant=variant)
                     self._events[j] = None
                     continue
                 st = self.streams[slot - 1]
                 st.wait_event(ready)
                 with torch.cuda.stream(st):
-                    y = self.members[j]._forward_impl(x)
+                    y = self.members[j]._forward_impl(x, variant=variant)
                     ev = torch.cuda.Event()
                     ev.record(st)
                 if not capturing:
@@ -474,7 +474,7 @@ class QuantLinear(nn.Module):
         return out
 
     # the cached descriptor holds ctypes pointers into this module's buffers: copies and pickles rebuild it lazily
-    _TRANSIENT = ('_desc', '_desc_ref', '_frag_keep', '_u_inv', '_ws_need', 'meta_host')
+    _TRANSIENT = ('_desc', '_desc_ref', '_frag_keep', '_u_inv', '_ws_need', 'meta_host', '_variants')
 
     def __getstate__(self):
         st = dict(self.__dict__)
@@ -550,7 +550,56 @@ class QuantLinear(nn.Module):
             self._desc = d
             self._desc_ref = C.byref(d)
             self._ws_need = {}
+            self._variants = {}
         return self._desc
+
+    # -- layout-order variants (the glue of the fused Llama stack moves the permutations into its own kernels) -------
+    def gather_index(self, side):
+        """The index vector of the K-side ('v': layout[l] = x[idx[l]]) or N-side ('u': y[j] = layout[idx[j]]) gather as an
+        int64 tensor, or None when it is the identity / the layer has no incoherence sides."""
+        self._descriptor()
+        if not self.incoh or self.meta_host[3 if side == 'v' else 4]:
+            return None
+        return getattr(self, f'{side}_idx').long()
+
+    def layout_variant_ok(self, skip_in=False, skip_out=False):
+        """Can forward_layout() skip the input gather (x already in V layout order) / the output gather (return y in U layout
+        order)?  Needs the 1/scaleWH folded into the V factors (no per-feature scale left at the gather) and no bias."""
+        self._descriptor()
+        if not self.incoh:
+            return False
+        if skip_in and self.rescale and not self.meta_host[2]:
+            return False
+        if skip_out and self.bias is not None:
+            return False
+        return True
+
+    def _variant(self, skip_in, skip_out):
+        self._descriptor()
+        key = (bool(skip_in), bool(skip_out))
+        v = self._variants.get(key)
+        if v is None:
+            if not self.layout_variant_ok(skip_in, skip_out):
+                raise ValueError('this layer cannot skip the requested gather (per-feature scale or bias at the gather)')
+            d = _lib.QuipLinearDesc()
+            C.memmove(C.byref(d), C.byref(self._desc), C.sizeof(d))
+            if skip_in:
+                d.V.idx = None
+            if skip_out:
+                d.U.idx, d.U.inv_idx = None, None
+            v = self._variants[key] = (d, C.byref(d), {})
+        return v
+
+    def forward_layout(self, x, skip_in=False, skip_out=False):
+        """forward() with the input taken in V layout order (skip_in: x[..., l] is already x_plain[..., v_idx[l]]) and / or the
+        output returned in U layout order (skip_out: y_plain[..., j] = y[..., u_idx[j]]).  The permutations are pure data
+        movement; callers that own the neighbouring elementwise kernels fold them there (quip_b200/fused.py)."""
+        if not (skip_in or skip_out):
+            return self.forward(x)
+        variant = (bool(skip_in), bool(skip_out))
+        if self._group is not None and x.is_cuda:          # siblings (gate / up) take the same variant, on their side streams
+            return self._group.get(self._group_index, x, variant=variant)
+        return self._forward_impl(x, variant=variant)
 
     # -- forward -------------------------------------------------------------------------------
     def forward(self, x):
@@ -558,7 +607,7 @@ class QuantLinear(nn.Module):
             return self._group.get(self._group_index, x)
         return self._forward_impl(x)
 
-    def _forward_impl(self, x):
+    def _forward_impl(self, x, variant=None):
         if x.shape[-1] != self.infeatures:
             raise ValueError(f'expected last dimension {self.infeatures}, got {tuple(x.shape)}')
         if not (x.is_cuda and self.qweight.is_cuda):
@@ -573,19 +622,22 @@ class QuantLinear(nn.Module):
         if M:
             lib = _lib.load()
             d = self._descriptor()
-            need = self._ws_need.get(M)                 # per token count: one C call the first time, a dict hit after
+            dref, ws_need = self._desc_ref, self._ws_need
+            if variant is not None:
+                d, dref, ws_need = self._variant(*variant)
+            need = ws_need.get(M)                       # per token count: one C call the first time, a dict hit after
             if need is None:
                 nb = C.c_size_t()
                 _lib.check(lib.quip_qlinear_workspace_bytes(C.byref(d), M, C.byref(nb)))
-                need = self._ws_need[M] = nb.value
+                need = ws_need[M] = nb.value
             stream = torch.cuda.current_stream(x.device)
             ws = _workspace(x.device, need, stream.cuda_stream)
             if x.device.index == torch.cuda.current_device():
-                _lib.check(lib.quip_qlinear_forward(self._desc_ref, xh.data_ptr(), y.data_ptr(), M, ws.data_ptr(), ws.numel(),
+                _lib.check(lib.quip_qlinear_forward(dref, xh.data_ptr(), y.data_ptr(), M, ws.data_ptr(), ws.numel(),
                                                     stream.cuda_stream))
             else:
                 with torch.cuda.device(x.device):
-                    _lib.check(lib.quip_qlinear_forward(self._desc_ref, xh.data_ptr(), y.data_ptr(), M, ws.data_ptr(),
+                    _lib.check(lib.quip_qlinear_forward(dref, xh.data_ptr(), y.data_ptr(), M, ws.data_ptr(),
                                                         ws.numel(), stream.cuda_stream))
         y = y.reshape(*x.shape[:-1], self.outfeatures)
         return y if dtype == torch.float16 else y.to(dtype)

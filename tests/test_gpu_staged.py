@@ -153,3 +153,59 @@ def test_batched_decode_token_counts_through_the_few_token_passes(K, N, bits, in
     finally:
         lib.quip_config(b'fewtok_max_m', 32)              # the library default
     assert lib.quip_config(b'fewtok_max_m', 33) != 0 and lib.quip_config(b'fewtok_max_m', 4) != 0
+
+
+@pytest.mark.parametrize('rows,n', [(1, 128), (7, 11008), (2048, 11008), (3, 4096), (5, 28672)])
+def test_silu_mul_gather_kernel(rows, n):
+    """quip_silu_mul_gather: SiLU(gate[ig]) * up[iu] with the packed index ig | iu << 16, bit-identical to gathering first and
+    calling quip_silu_mul."""
+    from quip_b200.fused import CudaGlue
+    g = torch.Generator().manual_seed(n + rows)
+    gate, up = _rand((rows, n), 1, 3.0), _rand((rows, n), 2)
+    ig, iu = torch.randperm(n, generator=g).cuda(), torch.randperm(n, generator=g).cuda()
+    comb = ig | (iu << 16)
+    idx = torch.where(comb >= 2 ** 31, comb - 2 ** 32, comb).to(torch.int32).contiguous()
+    ops = CudaGlue()
+    got = ops.silu_mul_gather(gate, up, idx)
+    want = ops.silu_mul(gate[:, ig].contiguous(), up[:, iu].contiguous())
+    assert torch.equal(got, want)
+
+
+def test_layout_variants_are_pure_permutations():
+    """QuantLinear.forward_layout: skipping the output gather returns y in U layout order (y_plain = y[..., u_idx]), skipping the
+    input gather takes x already in V layout order -- bit-identical data, every token-count route."""
+    from quip_b200 import quant as Q
+    from quip_b200.synth import synth_layer_parts
+    for (K, N) in [(4096, 11008), (11008, 4096), (4096, 4096)]:
+        tp = synth_layer_parts(K=K, N=N, bits=2, incoh='blocked', rescale=True, bias=False, seed=K + N)
+        ql = Q.QuantLinear(infeatures=K, outfeatures=N, **Q.spec_from_parts(tp)).cuda()
+        ql.pack_parts(tp)
+        assert ql.layout_variant_ok(True, True)
+        x = (torch.randn(300, K, device='cuda') * (1 + 3 * torch.rand(K, device='cuda'))).half()
+        vi, ui = ql.gather_index('v'), ql.gather_index('u')
+        for M in (1, 8, 24, 300):
+            y = ql(x[:M])
+            y_layout = ql.forward_layout(x[:M], skip_out=True)
+            assert torch.equal(y_layout[:, ui], y), (K, N, M, 'output gather')
+            y_in = ql.forward_layout(x[:M][:, vi].contiguous(), skip_in=True)
+            assert torch.equal(y_in, y), (K, N, M, 'input gather')
+            assert torch.equal(ql.forward_layout(x[:M][:, vi].contiguous(), skip_in=True, skip_out=True)[:, ui], y)
+
+
+def test_fused_stack_with_folded_gathers_is_bit_identical():
+    """llama_stack(fold_gathers=True): gate / up in layout order, one silu_mul_gather, down without its input gather -- the same
+    hidden states to the last bit as the stack with the separate gather kernels."""
+    from transformers import LlamaConfig
+    from quip_b200 import evalloop, fused
+    from quip_b200.synth import build_synthetic_model
+    cfg = LlamaConfig(hidden_size=4096, intermediate_size=11008, num_hidden_layers=1, num_attention_heads=32,
+                      num_key_value_heads=32, vocab_size=320, max_position_embeddings=256)
+    model = build_synthetic_model(cfg, torch.device('cuda:0'), bits=2, incoh='blocked', rescale=True, seed=5, seqlen=200)
+    ids = torch.randint(0, 320, (1, 200), generator=torch.Generator().manual_seed(3)).cuda()
+    with torch.no_grad():
+        h, kw = evalloop.layer_inputs(model, evalloop.LLAMA, ids)
+        layers = list(model.model.layers)
+        assert fused.mlp_layout_plan(layers[0].mlp) is not None
+        a = fused.llama_stack(layers, h.clone(), kw, fold_gathers=False)
+        b = fused.llama_stack(layers, h.clone(), kw, fold_gathers=True)
+    assert torch.equal(a, b)
