@@ -24,6 +24,8 @@ constexpr int LQ_BLOCK = 128;         // columns per block (vector_balance.py:22
 constexpr int LQ_LANES = 4;           // threads cooperating on one row
 constexpr int LQ_ROWS = 64;           // rows per CTA
 constexpr int LQ_THREADS = LQ_ROWS * LQ_LANES;
+constexpr int LQ_LD = LQ_ROWS + 8;   // row pitch of the per-column error / s arrays: the 4 lanes of a row read 4 consecutive
+                                      // columns, 8 rows per warp -> bank 8 * lane + row, conflict-free (pitch 64: 4-way)
 
 __device__ __forceinline__ float lane_sum(float v) {
 #pragma unroll
@@ -40,7 +42,7 @@ ldlq_block_kernel(const float* __restrict__ baseT, const float* __restrict__ wT,
                   float* __restrict__ qT, float* __restrict__ errT, int m, int ld, int cnt, float top) {
   extern __shared__ float sm[];
   float* Ls = sm;                                 // [cnt][cnt + 1] transposed: Ls[j * (cnt+1) + j'] = Lb[j'][j]
-  float* E = sm + cnt * (cnt + 1);                // [cnt][LQ_ROWS]: errors of the columns already rounded
+  float* E = sm + cnt * (cnt + 1);                // [cnt][LQ_LD]: errors of the columns already rounded
   const int tid = threadIdx.x, lane = tid % LQ_LANES, rl = tid / LQ_LANES;
   const int row = blockIdx.x * LQ_ROWS + rl;
   for (int i = tid; i < cnt * cnt; i += LQ_THREADS) {
@@ -55,10 +57,10 @@ ldlq_block_kernel(const float* __restrict__ baseT, const float* __restrict__ wT,
     const float* lrow = Ls + j * (cnt + 1);
     int jp = j + 1 + lane;
     for (; jp + LQ_LANES < cnt; jp += 2 * LQ_LANES) {
-      acc0 = fmaf(E[jp * LQ_ROWS + rl], lrow[jp], acc0);
-      acc1 = fmaf(E[(jp + LQ_LANES) * LQ_ROWS + rl], lrow[jp + LQ_LANES], acc1);
+      acc0 = fmaf(E[jp * LQ_LD + rl], lrow[jp], acc0);
+      acc1 = fmaf(E[(jp + LQ_LANES) * LQ_LD + rl], lrow[jp + LQ_LANES], acc1);
     }
-    if (jp < cnt) acc0 = fmaf(E[jp * LQ_ROWS + rl], lrow[jp], acc0);
+    if (jp < cnt) acc0 = fmaf(E[jp * LQ_LD + rl], lrow[jp], acc0);
     const float fb = lane_sum(acc0 + acc1);
     float e = 0.f;
     if (live && lane == 0) {
@@ -69,7 +71,7 @@ ldlq_block_kernel(const float* __restrict__ baseT, const float* __restrict__ wT,
       qT[(size_t)j * ld + row] = q;
       errT[(size_t)j * ld + row] = e;
     }
-    if (lane == 0) E[j * LQ_ROWS + rl] = e;
+    if (lane == 0) E[j * LQ_LD + rl] = e;
     __syncwarp();                                 // the LANES threads of a row sit in one warp
   }
 }
@@ -83,7 +85,7 @@ greedy_block_kernel(const float* __restrict__ preT, const float* __restrict__ Hb
                     float* __restrict__ sT, int m, int ld, int cnt) {
   extern __shared__ float sm[];
   float* Hs = sm;                                 // [cnt][cnt + 1]: Hs[i * (cnt+1) + j] = Hb[j][i] (= Hb[i][j])
-  float* S = sm + cnt * (cnt + 1);                // [cnt][LQ_ROWS]: the row's s over the block, updated in place
+  float* S = sm + cnt * (cnt + 1);                // [cnt][LQ_LD]: the row's s over the block, updated in place
   const int tid = threadIdx.x, lane = tid % LQ_LANES, rl = tid / LQ_LANES;
   const int row = blockIdx.x * LQ_ROWS + rl;
   const bool live = row < m;
@@ -93,7 +95,7 @@ greedy_block_kernel(const float* __restrict__ preT, const float* __restrict__ Hb
   }
   for (int i = tid; i < cnt * LQ_ROWS; i += LQ_THREADS) {
     const int j = i / LQ_ROWS, r = i - j * LQ_ROWS, gr = blockIdx.x * LQ_ROWS + r;
-    S[j * LQ_ROWS + r] = gr < m ? sT[(size_t)j * ld + gr] : 0.f;
+    S[j * LQ_LD + r] = gr < m ? sT[(size_t)j * ld + gr] : 0.f;
   }
   __syncthreads();
   for (int i = cnt - 1; i >= 0; --i) {
@@ -101,13 +103,13 @@ greedy_block_kernel(const float* __restrict__ preT, const float* __restrict__ Hb
     const float* hrow = Hs + i * (cnt + 1);
     int j = lane;
     for (; j + LQ_LANES < cnt; j += 2 * LQ_LANES) {
-      acc0 = fmaf(S[j * LQ_ROWS + rl], hrow[j], acc0);
-      acc1 = fmaf(S[(j + LQ_LANES) * LQ_ROWS + rl], hrow[j + LQ_LANES], acc1);
+      acc0 = fmaf(S[j * LQ_LD + rl], hrow[j], acc0);
+      acc1 = fmaf(S[(j + LQ_LANES) * LQ_LD + rl], hrow[j + LQ_LANES], acc1);
     }
-    if (j < cnt) acc0 = fmaf(S[j * LQ_ROWS + rl], hrow[j], acc0);
+    if (j < cnt) acc0 = fmaf(S[j * LQ_LD + rl], hrow[j], acc0);
     const float dot = lane_sum(acc0 + acc1);
     if (lane == 0) {
-      float snew = S[i * LQ_ROWS + rl];
+      float snew = S[i * LQ_LD + rl];
       if (live) {
         const float hs = preT[(size_t)i * ld + row] + dot;
         const float cur = wrT[(size_t)i * ld + row];
@@ -116,13 +118,13 @@ greedy_block_kernel(const float* __restrict__ preT, const float* __restrict__ Hb
         snew -= move;
         sT[(size_t)i * ld + row] = snew;
       }
-      S[i * LQ_ROWS + rl] = snew;
+      S[i * LQ_LD + rl] = snew;
     }
     __syncwarp();
   }
 }
 
-size_t lq_smem(int cnt) { return ((size_t)cnt * (cnt + 1) + (size_t)cnt * LQ_ROWS) * sizeof(float); }
+size_t lq_smem(int cnt) { return ((size_t)cnt * (cnt + 1) + (size_t)cnt * LQ_LD) * sizeof(float); }
 
 template <class K>
 int lq_prepare(K kern, int cnt) {

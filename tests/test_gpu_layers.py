@@ -208,7 +208,7 @@ def test_one_launch_sides_for_a_handful_of_tokens(K, N, bits, incoh, bias):
             assert float((y1 - want[:M]).norm() / want[:M].norm()) < 1e-3, (M, 'vs fp32 restatement')
             assert float((y1 - y0).norm() / y0.norm()) < 1e-3, (M, 'vs the two-pass route')     # that one rounds the intermediate to fp16
             assert torch.equal(y1, ql(x[:M]).float())
-            assert launches <= 5, (M, launches)
+            assert launches <= 7, (M, launches)
             if max(K, N) <= 4096 or (M == 1 and max(K, N) <= 11008):   # both sides fit shared memory (tokens + factor rows)
                 assert launches == 3, (M, launches)
     finally:
