@@ -150,12 +150,12 @@ constexpr int SG_THREADS = 512;
 
 __global__ void __launch_bounds__(SG_THREADS)
 silu_mul_gather_kernel(const __half* __restrict__ g, const __half* __restrict__ u, const uint32_t* __restrict__ idx,
-                       __half* __restrict__ out, int64_t rows, int n) {
+                       __half* __restrict__ out, int64_t rows, int n, int rpc) {
   extern __shared__ __align__(16) unsigned char sg_raw[];
-  __half* gs = reinterpret_cast<__half*>(sg_raw);                 // [SG_ROWS][n]
-  __half* us = gs + (size_t)SG_ROWS * n;                          // [SG_ROWS][n]
-  const int64_t r0 = (int64_t)blockIdx.x * SG_ROWS;
-  const int nr = (int)((rows - r0) < SG_ROWS ? (rows - r0) : SG_ROWS);
+  __half* gs = reinterpret_cast<__half*>(sg_raw);                 // [rpc][n]   (rpc <= SG_ROWS token rows per CTA)
+  __half* us = gs + (size_t)rpc * n;                              // [rpc][n]
+  const int64_t r0 = (int64_t)blockIdx.x * rpc;
+  const int nr = (int)((rows - r0) < rpc ? (rows - r0) : rpc);
   const int nvec = n >> 3;
   for (int c = threadIdx.x; c < nr * nvec; c += SG_THREADS) {
     const int r = c / nvec, v = c - r * nvec;
@@ -255,7 +255,8 @@ extern "C" int quip_silu_mul_gather(const void* gate, const void* up, const uint
   QUIP_CHECK_ARG(aligned16(gate) && aligned16(up) && aligned16(idx) && aligned16(out), "quip_silu_mul_gather: pointers must be 16-byte aligned");
   QUIP_CHECK_ARG(gate != out && up != out, "quip_silu_mul_gather: out must not alias the inputs (it is a permutation)");
   if (rows == 0) return QUIP_OK;
-  const size_t smem = (size_t)2 * SG_ROWS * n * sizeof(__half);
+  const int rpc = (size_t)2 * SG_ROWS * n * sizeof(__half) <= 110 * 1024 ? SG_ROWS : 1;      // two CTAs per SM when they fit
+  const size_t smem = (size_t)2 * rpc * n * sizeof(__half);
   QUIP_CHECK_ARG(smem <= 220 * 1024, "quip_silu_mul_gather: width %d does not fit shared memory", n);
   static size_t done[64] = {0};
   int dev = 0;
@@ -264,8 +265,8 @@ extern "C" int quip_silu_mul_gather(const void* gate, const void* up, const uint
     QUIP_CUDA(cudaFuncSetAttribute(silu_mul_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     done[dev & 63] = smem;
   }
-  silu_mul_gather_kernel<<<(unsigned)ceil_div(rows, SG_ROWS), SG_THREADS, smem, (cudaStream_t)stream>>>(
-      (const __half*)gate, (const __half*)up, idx, (__half*)out, rows, n);
+  silu_mul_gather_kernel<<<(unsigned)ceil_div(rows, rpc), SG_THREADS, smem, (cudaStream_t)stream>>>(
+      (const __half*)gate, (const __half*)up, idx, (__half*)out, rows, n, rpc);
   QUIP_LAUNCHED("silu_mul_gather_kernel");
   return QUIP_OK;
 }

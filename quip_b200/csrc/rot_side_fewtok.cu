@@ -92,26 +92,34 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
   __half* tmp = reinterpret_cast<__half*>(sm_raw + pl.tmp);                        // [M][n]
   uint16_t* sidx = reinterpret_cast<uint16_t*>(sm_raw + pl.sidx);                  // [n]
 
+  // Index arithmetic without divisions (they dominated the instruction count of a first version): the second-pass block c1
+  // takes element c1 of EVERY first-pass block, so input j of block c1 is row i = c1 of first-pass block c0 = j
+  // (nblk0 == p1, nblk1 == p0); loops are two-dimensional (warp x lane) instead of flat with / and %.
+  constexpr int NW = SF_THREADS / 32;
+  const bool multi = blocks_per_cta > 1;                                          // only for 16-wide second-pass blocks
+
   // ---- everything that does not depend on the previous kernel is requested now: this CTA's factor rows travel to
   // shared memory (cp.async) and the gather index is read while the previous kernel drains ----
   {
     const int cpr0 = p0 >> 3;                                                     // 16-byte pieces per first-pass row
-    for (int c = tid; c < ndots * cpr0; c += SF_THREADS) {
-      const int d = c / cpr0, pc = c - d * cpr0, bl = d / p1, j = d - bl * p1, c1 = c1_first + bl;
+    for (int d = warp; d < ndots; d += NW) {
+      const int bl = multi ? d / p1 : 0, j = d - bl * p1, c1 = c1_first + bl;
       if (c1 < P1.nblk) {
-        const int pos = pos_of(P1, c1, j);                                        // layout position of this input
-        const int c0 = P0.strided ? pos % P0.nblk : pos / p0, i = P0.strided ? pos / P0.nblk : pos % p0;
-        cp_async16(F0s + (size_t)d * p0 + 8 * pc, P0.F + ((size_t)(P0.shared ? 0 : c0) * p0 + i) * p0 + 8 * pc);
+        const __half* src = P0.F + ((size_t)(P0.shared ? 0 : j) * p0 + c1) * p0;  // row c1 of first-pass block j
+        for (int pc = lane; pc < cpr0; pc += 32) cp_async16(F0s + (size_t)d * p0 + 8 * pc, src + 8 * pc);
       }
     }
     const int cpr1 = p1 >> 3;
-    for (int c = tid; c < nout * cpr1; c += SF_THREADS) {
-      const int o = c / cpr1, pc = c - o * cpr1, bl = o / nrows, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
-      if (c1 < P1.nblk) cp_async16(F1s + (size_t)o * p1 + 8 * pc, P1.F + ((size_t)(P1.shared ? 0 : c1) * p1 + r) * p1 + 8 * pc);
+    for (int o = warp; o < nout; o += NW) {
+      const int bl = multi ? o / nrows : 0, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
+      if (c1 < P1.nblk) {
+        const __half* src = P1.F + ((size_t)(P1.shared ? 0 : c1) * p1 + r) * p1;
+        for (int pc = lane; pc < cpr1; pc += 32) cp_async16(F1s + (size_t)o * p1 + 8 * pc, src + 8 * pc);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     for (int o = tid; o < nout; o += SF_THREADS) {                                // where the outputs go (scatter index, bias)
-      const int bl = o / nrows, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
+      const int bl = multi ? o / nrows : 0, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
       int dst = 0;
       float bs = 0.f;
       if (c1 < P1.nblk) {
@@ -148,7 +156,7 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
 #pragma unroll
     for (int u = 0; u < SF_MLP; ++u) {
       const int c = base + u * SF_THREADS;
-      if (c < M * (n >> 3)) v[u] = *reinterpret_cast<const uint4*>(in + (size_t)c * 8);      // (m, f0) = (c / (n/8), 8 (c % (n/8)))
+      if (c < M * (n >> 3)) v[u] = *reinterpret_cast<const uint4*>(in + (size_t)c * 8);      // row m = c / (n/8), features 8 (c % (n/8))
     }
 #pragma unroll
     for (int u = 0; u < SF_MLP; ++u) {
@@ -165,13 +173,22 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
     }
   }
   __syncthreads();
-  // ---- ... then into first-pass block order: xs0[m][c0][k] = x[m][idx[pos0(c0, k)]].  The loop runs over layout
-  // positions q (index reads conflict-free); the row padding makes the transposing stores conflict-free too ----
-  for (int q = tid; q < n; q += SF_THREADS) {
-    const int c0 = P0.strided ? q % P0.nblk : q / p0, k = P0.strided ? q / P0.nblk : q % p0;
-    const int src = sidx[q];
+  // ---- ... then into first-pass block order: xs0[m][c0][k] = x[m][idx[pos0(c0, k)]]: consecutive lanes take consecutive
+  // layout positions q (index reads conflict-free); the row padding makes the transposing stores conflict-free too ----
+  if (P0.strided) {                                                               // q = k * nblk0 + c0
+    for (int k = warp; k < p0; k += NW)
+      for (int c0 = lane; c0 < P0.nblk; c0 += 32) {
+        const int src = sidx[k * P0.nblk + c0];
 #pragma unroll
-    for (int m = 0; m < M; ++m) xs0[((size_t)m * P0.nblk + c0) * pl.xld + k] = tmp[(size_t)m * n + src];
+        for (int m = 0; m < M; ++m) xs0[((size_t)m * P0.nblk + c0) * pl.xld + k] = tmp[(size_t)m * n + src];
+      }
+  } else {                                                                        // q = c0 * p0 + k
+    for (int c0 = warp; c0 < P0.nblk; c0 += NW)
+      for (int k = lane; k < p0; k += 32) {
+        const int src = sidx[c0 * p0 + k];
+#pragma unroll
+        for (int m = 0; m < M; ++m) xs0[((size_t)m * P0.nblk + c0) * pl.xld + k] = tmp[(size_t)m * n + src];
+      }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
@@ -179,17 +196,15 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
   // ---- first pass, only the rows this CTA's second-pass blocks consume: `lpd` lanes per dot product ----
   const int lpd = p0 >= 64 ? 32 : (p0 >= 32 ? 16 : 8);                            // p0 is a multiple of 16
   const int dpw = 32 / lpd, sub = lane / lpd, ll = lane - sub * lpd;
-  for (int d0 = warp * dpw; d0 < ndots; d0 += (SF_THREADS / 32) * dpw) {
+  for (int d0 = warp * dpw; d0 < ndots; d0 += NW * dpw) {
     const int d = d0 + sub;
-    const int bl = d / p1, j = d - bl * p1, c1 = c1_first + bl;
+    const int bl = multi ? d / p1 : 0, j = d - bl * p1, c1 = c1_first + bl;
     float acc[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) acc[m] = 0.f;
     if (d < ndots && c1 < P1.nblk) {
-      const int pos = pos_of(P1, c1, j);
-      const int c0 = P0.strided ? pos % P0.nblk : pos / p0;
       const __half* frow = F0s + (size_t)d * p0;
-      const __half* xb = xs0 + (size_t)c0 * pl.xld;
+      const __half* xb = xs0 + (size_t)j * pl.xld;                                // first-pass block c0 = j
 #pragma unroll 4
       for (int k = 2 * ll; k < p0; k += 2 * lpd) {
         const float2 f = __half22float2(*reinterpret_cast<const __half2*>(frow + k));
@@ -214,7 +229,7 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
   // ---- second pass: rows [rt * rows_per_cta, ...) of each of this CTA's blocks, a group of 4 lanes per output row ----
   for (int o4 = tid; o4 < nout * 4; o4 += SF_THREADS) {                           // nout * 4 is a multiple of 64: whole warps
     const int o = o4 >> 2, part = o4 & 3;
-    const int bl = o / nrows, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
+    const int bl = multi ? o / nrows : 0, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
     float acc[M];
 #pragma unroll
     for (int m = 0; m < M; ++m) acc[m] = 0.f;
