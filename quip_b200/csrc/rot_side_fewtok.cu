@@ -30,7 +30,8 @@ namespace quip {
 
 namespace {
 
-constexpr int SF_THREADS = 256;
+constexpr int SF_THREADS = 1024;      // the work is a long chain of short dependent steps: many warps hide each other's latencies
+constexpr int SF_PL = 8;              // lanes per output row in the second pass
 constexpr int SF_MAXTOK = 8;
 constexpr int SF_MLP = 8;             // independent 16-byte loads a thread keeps in flight in the staging loops
 constexpr int SF_ROWS = 32;           // second-pass output rows per CTA when its blocks are wider than 64
@@ -227,8 +228,8 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
   __syncthreads();
 
   // ---- second pass: rows [rt * rows_per_cta, ...) of each of this CTA's blocks, a group of 4 lanes per output row ----
-  for (int o4 = tid; o4 < nout * 4; o4 += SF_THREADS) {                           // nout * 4 is a multiple of 64: whole warps
-    const int o = o4 >> 2, part = o4 & 3;
+  for (int o4 = tid; o4 < nout * SF_PL; o4 += SF_THREADS) {                       // nout * SF_PL is a multiple of 128: whole warps
+    const int o = o4 / SF_PL, part = o4 % SF_PL;
     const int bl = multi ? o / nrows : 0, r = rt * rows_per_cta + (o - bl * nrows), c1 = c1_first + bl;
     float acc[M];
 #pragma unroll
@@ -238,7 +239,7 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
       const __half* frow = F1s + (size_t)o * p1;
       const float* tb = ts + (size_t)bl * p1 * M;
 #pragma unroll 2
-      for (int k = 8 * part; k < p1; k += 32) {                                   // 16-byte pieces of the row, interleaved over the 4 lanes
+      for (int k = 8 * part; k < p1; k += 8 * SF_PL) {                            // 16-byte pieces of the row, interleaved over the lanes
         const uint4 v = *reinterpret_cast<const uint4*>(frow + k);
         const __half2* h2 = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
@@ -252,8 +253,8 @@ side_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, int 
     }
 #pragma unroll
     for (int m = 0; m < M; ++m) {
-      acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 1);
-      acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], 2);
+#pragma unroll
+      for (int sh = SF_PL / 2; sh; sh >>= 1) acc[m] += __shfl_xor_sync(0xffffffffu, acc[m], sh);
     }
     if (live && part == 0) {
       const int dst = dst_s[o];
