@@ -189,7 +189,8 @@ int quip_timing_read(int path, double* total_ms, int64_t* launches, double* flop
  *   "side_fused" (1)  M > 8: a whole incoherence side in one kernel when both blocks are 32/64 wide and factors_frag is set
  *   "fewtok" (1)      M <= 8: few-token pass / gather kernels (fused input gather, output scatter + bias)
  *   "fewtok_max_m" (32) 8..32: token count up to which the few-token passes run (batched decode)
- *   "side_fewtok" (1) M <= 8: both passes of a side (+ gather / scatter, bias) in one launch: side, contraction, side
+ *   "side_fewtok" (0) M <= 8: both passes of a side (+ gather / scatter, bias) in one launch: side, contraction, side
+ *                     (ablation: measured slower than the two-pass route, see profiles/README.md)
  *   "pdl" (1)         programmatic dependent launch along the few-token chain
  *   "gemv" (1)        M <= 8: whole-K qgemv kernels (0: split-K mma.sync kernel)
  *   "gv_int" (1)      qgemv: int8 tensor-core path for 2-/4-bit and <= 5 tokens (0: fp16 path)

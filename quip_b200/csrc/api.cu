@@ -56,7 +56,9 @@ static int g_use_ts = 0;         // route 2-bit big-M contractions to the TS-mod
 static int g_side_fused = 1;     // many tokens: a whole side (gather + both passes [+ row sums]) in one kernel when the blocks allow
 static int g_pdl = 1;            // few-token kernels: programmatic dependent launch (weights prefetched under the previous kernel)
 static int g_use_gemv = 1;       // few-token contractions: whole-K qgemv kernel (0: the split-K kernel)
-static int g_side_fewtok = 1;    // <= 8 tokens: both passes of a side in ONE launch (rot_side_fewtok.cu), 3 launches per linear
+static int g_side_fewtok = 0;    // <= 8 tokens: both passes of a side in ONE launch (rot_side_fewtok.cu), 3 launches per linear.
+                                 // Correct on every shape but measured SLOWER than two pass launches (every CTA stages the whole
+                                 // token vector): an ablation, off by default (profiles/README.md)
 
 // Launch with the programmatic-stream-serialization attribute: the kernel may start while its predecessor in
 // the stream drains; everything it does before griddepcontrol.wait must be independent of that predecessor.

@@ -212,4 +212,4 @@ def test_one_launch_sides_for_a_handful_of_tokens(K, N, bits, incoh, bias):
             if max(K, N) <= 4096 or (M == 1 and max(K, N) <= 11008):   # both sides fit shared memory (tokens + factor rows)
                 assert launches == 3, (M, launches)
     finally:
-        lib.quip_config(b'side_fewtok', 1)
+        lib.quip_config(b'side_fewtok', 0)                     # the library default (the one-launch route is an ablation)

@@ -266,7 +266,7 @@ def main():
                     r = bench_layer(N, K, M, 2, 'blocked', peaks, copies=4); r['pdl'] = pdl; r['side_fewtok'] = sf
                     res.append(r); print(r, flush=True)
         lib.quip_config(b'pdl', 1)
-        lib.quip_config(b'side_fewtok', 1)
+        lib.quip_config(b'side_fewtok', 0)
     if 'side' in what:
         lib = _lib.load()
         for sf in (0, 1):
