@@ -539,7 +539,8 @@ def pp_main(a, base, rank, world):
             dist.barrier()
             torch.cuda.synchronize()
         # stage body alone (device time of one replay): the pipeline's steady state is paced by the slowest stage
-        stage_ms = _device_ms(stage._compute, reps=3, warm=2)
+        est = _device_ms(stage._compute, reps=2, warm=2)
+        stage_ms = _device_ms(stage._compute, reps=max(3, min(60, int(2000.0 / max(est, 1e-3)))), warm=0)   # ~2 s: sustained clocks
         stage.run([ids_host[i] for i in range(a.warmup)])
         barrier()
         launches0 = lib.quip_launch_count()
@@ -670,8 +671,6 @@ def main():
     dev = torch.device('cuda', local)
     torch.cuda.set_device(dev)
     lib = _lib.load()
-    if os.environ.get('QUIP_TC2') == '1':
-        lib.quip_config(b'tc2', 1)
 
     cfg = model_config(a.model) if not a.layers else model_config(a.model, num_hidden_layers=a.layers)
     model = build_synthetic_model(cfg, dev, bits=2, incoh='blocked', rescale=True, seed=rank, seqlen=SEQ)
@@ -836,8 +835,7 @@ def main():
     out = dict(base, value=value, ms_per_step=ms / a.steps, dtype='f16', impl='ours', gpu_launches=int(launches),
                e2e=dict(value=e2e_value, unit='tokens/s', h2d_bytes_per_step=SEQ * 8, d2h_bytes_per_step=4,
                         api='quip_b200.llama.llama_eval' if family == 'llama' else 'quip_b200.opt.opt_eval'),
-               roofline=dict(bound='tensor', kernel=('qgemm_tc2_kernel<2> (tcgen05 cta_group::2 packed GEMM)' if os.environ.get('QUIP_TC2') == '1'
-                                     else 'qgemm_tc_kernel<2,256> (tcgen05 packed GEMM)'), achieved=achieved,
+               roofline=dict(bound='tensor', kernel='qgemm_tc_kernel<2,256> (tcgen05 packed GEMM)', achieved=achieved,
                              peak=pk['tflops_sustained'], unit='TFLOP/s', frac=(achieved / pk['tflops_sustained']) if achieved else None,
                              traffic=traffic, traffic_note=traffic_note, launches_timed=int(tn.value), kernel_ms_per_step=tms.value / a.steps,
                              share_of_step=tms.value / serial_ms,

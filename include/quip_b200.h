@@ -103,8 +103,7 @@ int quip_qlinear_workspace_bytes(const QuipLinearDesc* d, int64_t M, size_t* out
 /* Building blocks (also exported for tests and micro-benchmarks). */
 /* z (M,N) fp16 = x2 (M,K) fp16 contracted with the packed matrix + affine epilogue (+bias if given).
  * xsum (M) fp32 row sums of x2, required unless QUIP_FLAG_SYMMETRIC.  path: 0 auto, 1 few-token kernels (32-token
- * chunks; needs the workspace), 2 tcgen05 kernel, 3 tcgen05 2-CTA (cta_group::2) kernel, 4 tcgen05 TS-mode kernel (weights in
- * TMEM, 2-bit only). */
+ * chunks; needs the workspace), 2 tcgen05 kernel. */
 int quip_qgemm(const QuipLinearDesc* d, const void* x2, const float* xsum, const void* bias,
                void* z, int64_t M, int path, void* workspace, size_t workspace_bytes, void* stream);
 int quip_rowsum(const void* x, float* xsum, int64_t M, int32_t K, void* stream);
@@ -196,7 +195,6 @@ int quip_timing_read(int path, double* total_ms, int64_t* launches, double* flop
  *   "gv_int" (1)      qgemv: int8 tensor-core path for 2-/4-bit and <= 5 tokens (0: fp16 path)
  *   "gv_tma" (1), "gv_cw" (16), "gv_rbc" (0 = auto), "gv_persist" (1)   variants of the cooperative int8 kernel
  *   "gv_stream" (32)  streaming int8 kernel when N/16 >= value * SMs (0: never)
- *   "tc2" / "ts" (0)  route contractions with M > 128 to the 2-CTA / TS-mode tcgen05 kernels
  *   "gather_rows", "pass_min_tiles"   tune the many-token un-projection kernels */
 int quip_config(const char* key, int value);
 

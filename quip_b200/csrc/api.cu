@@ -32,10 +32,6 @@ int qgemv(const QuipLinearDesc* d, const __half* x, const __half* bias, __half* 
 bool qgemv_fits(int K, int M, int bits);
 int qgemm_tc(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
              cudaStream_t s);
-int qgemm_tc2(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
-              cudaStream_t s);
-int qgemm_ts(const QuipLinearDesc* d, const __half* x, const float* xsum, const __half* bias, __half* z, int M,
-             cudaStream_t s);
 
 extern int g_gather_rows, g_pass_min_tiles, g_fewtok;   // rot.cu
 extern int g_fewtok_max_m;                               // rot_fewtok.cu: token count up to which the few-token kernels run (8)
@@ -51,8 +47,6 @@ int side_fewtok(const QuipSide* sd, const __half* in, __half* out, int64_t M, in
                 const float* in_scale, const int32_t* out_inv, const __half* out_bias, cudaStream_t s);
 
 // tuning knobs (quip_config)
-static int g_use_tc2 = 0;        // route big-M contractions to the 2-CTA kernel
-static int g_use_ts = 0;         // route 2-bit big-M contractions to the TS-mode (A in TMEM) kernel
 static int g_side_fused = 1;     // many tokens: a whole side (gather + both passes [+ row sums]) in one kernel when the blocks allow
 static int g_pdl = 1;            // few-token kernels: programmatic dependent launch (weights prefetched under the previous kernel)
 static int g_use_gemv = 1;       // few-token contractions: whole-K qgemv kernel (0: the split-K kernel)
@@ -143,7 +137,7 @@ static int run_qgemm_untimed(const QuipLinearDesc* d, const __half* x2, const fl
 static int run_qgemm(const QuipLinearDesc* d, const __half* x2, const float* xsum, const __half* bias, __half* z,
                      int64_t M, int path, unsigned char* ws, const WsPlan& p, cudaStream_t s) {
   if (path == 0)
-    path = M <= SKINNY_MAX_M ? 1 : ((g_use_ts && d->bits == 2 && M > 128) ? 4 : ((g_use_tc2 && M > 128) ? 3 : 2));
+    path = M <= SKINNY_MAX_M ? 1 : 2;
   if (!g_timing || g_timed.size() >= TIMED_MAX) return run_qgemm_untimed(d, x2, xsum, bias, z, M, path, ws, p, s);
   TimedLaunch t;
   if (!g_pool.empty()) {
@@ -153,7 +147,7 @@ static int run_qgemm(const QuipLinearDesc* d, const __half* x2, const float* xsu
     QUIP_CUDA(cudaEventCreate(&t.e0));
     QUIP_CUDA(cudaEventCreate(&t.e1));
   }
-  t.path = path >= 3 ? 2 : path;
+  t.path = path;
   t.flops = 2.0 * (double)M * d->N * d->K;
   t.bytes = (double)d->N * d->K * d->bits / 8.0 + 2.0 * (double)M * (d->K + d->N);
   QUIP_CUDA(cudaEventRecord(t.e0, s));
@@ -182,8 +176,6 @@ static int run_qgemm_untimed(const QuipLinearDesc* d, const __half* x2, const fl
   }
   const bool need_xsum = !(d->flags & QUIP_FLAG_SYMMETRIC);
   QUIP_CHECK_ARG(!need_xsum || xsum, "asymmetric grid needs the row sums of x");
-  if (path == 3) return qgemm_tc2(d, x2, xsum, bias, z, (int)M, s);
-  if (path == 4) return qgemm_ts(d, x2, xsum, bias, z, (int)M, s);
   return qgemm_tc(d, x2, xsum, bias, z, (int)M, s);
 }
 
@@ -197,8 +189,6 @@ extern "C" int64_t quip_launch_count(void) { return g_launches.load(); }
 
 extern "C" int quip_config(const char* key, int value) {
   QUIP_CHECK_ARG(key != nullptr, "null key");
-  if (!strcmp(key, "tc2")) { g_use_tc2 = value; return QUIP_OK; }
-  if (!strcmp(key, "ts")) { g_use_ts = value; return QUIP_OK; }
   if (!strcmp(key, "side_fused")) { g_side_fused = value; return QUIP_OK; }
   if (!strcmp(key, "side_fewtok")) { g_side_fewtok = value; return QUIP_OK; }
   if (!strcmp(key, "pdl")) { g_pdl = value; return QUIP_OK; }
@@ -259,7 +249,7 @@ extern "C" int quip_qgemm(const QuipLinearDesc* d, const void* x2, const float* 
   if (int e = check_desc(d)) return e;
   QUIP_CHECK_ARG(x2 && z && M > 0 && M < (1ll << 31), "bad arguments");
   WsPlan p = plan_ws(d, M);
-  QUIP_CHECK_ARG(path >= 0 && path <= 4, "path must be 0..4");
+  QUIP_CHECK_ARG(path >= 0 && path <= 2, "path must be 0 (auto), 1 (few-token kernels) or 2 (tcgen05)");
   // the few-token kernels keep split-K partials + arrival counters in the workspace (path 1 loops 32-token chunks for any M)
   if (path == 1 || (path == 0 && M <= SKINNY_MAX_M)) {
     if (!workspace || workspace_bytes < p.total) {

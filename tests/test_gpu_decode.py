@@ -30,10 +30,27 @@ def test_graph_decoder_matches_eager_hf_decode(kv_heads):
         dec.reset()
         dec.capture()
         graph = [dec.step(ids[0, i:i + 1])[0].float().clone() for i in range(ids.shape[1])]
-    for i, (w, e, g) in enumerate(zip(want, eager, graph)):
+        # control: the HF decode against ITSELF with one-ulp flips in 3e-5 of its norm outputs.  The decoder restates the
+        # fp16 glue (another attention kernel over the static cache, another order of the same roundings), and a random-init
+        # model amplifies any such noise: the graph decode has to stay within 3x of what the HF loop does to itself.
+        import bench
+        norms = [m for layer in model.model.layers for m in (layer.input_layernorm, layer.post_attention_layernorm)] + [model.model.norm]
+        past, ctrl = None, []
+        for i in range(ids.shape[1]):
+            hooks = bench._ulp_flip_hooks(norms, 3e-5, seed=i)
+            try:
+                out = model(ids[:, i:i + 1], past_key_values=past, use_cache=True)
+            finally:
+                for hk in hooks:
+                    hk.remove()
+            past = out.past_key_values
+            ctrl.append(out.logits[0, -1].float())
+    worst = control = 0.0
+    for i, (w, e, g, c) in enumerate(zip(want, eager, graph, ctrl)):
         assert torch.equal(e, g), i                                   # replay == the recorded computation
-        err = float((g - w).norm() / w.norm())
-        assert err < 2e-2, (i, err)                                   # fp16 glue restated: same numbers up to rounding
+        worst = max(worst, float((g - w).norm() / w.norm()))
+        control = max(control, float((c - w).norm() / w.norm()))
+    assert worst < max(2e-3, 3.0 * control), (worst, control)         # round 1 accepted 2e-2 outright
     with pytest.raises(ValueError):
         for _ in range(40):
             dec.step(ids[0, :1])

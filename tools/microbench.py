@@ -218,10 +218,6 @@ def main():
     if 'prof_tc' in what:
         res.append(bench_qgemm(4096, 4096, 2048, 2, 2, 2, peaks)); print(res[-1], flush=True)
         res.append(bench_qgemm(11008, 4096, 2048, 2, 2, 2, peaks)); print(res[-1], flush=True)
-    if 'tc2' in what:
-        for (N, K) in shapes:
-            for path in (2, 3, 4):
-                res.append(bench_qgemm(N, K, 2048, 2, path, 2, peaks)); print(res[-1], flush=True)
     if 'tune' in what:
         lib = _lib.load()
         for mt in (1, 2, 4):
@@ -234,10 +230,6 @@ def main():
             for n in (4096, 11008):
                 r = bench_gather(n, 2048); r['gather_rows'] = R; res.append(r); print(r, flush=True)
         lib.quip_config(b'gather_rows', 0)
-    if 'prof_ts' in what:
-        res.append(bench_qgemm(4096, 4096, 2048, 2, 4, 2, peaks)); print(res[-1], flush=True)
-    if 'prof_tc2' in what:
-        res.append(bench_qgemm(4096, 4096, 2048, 2, 3, 2, peaks)); print(res[-1], flush=True)
     if 'prof_skinny' in what:
         res.append(bench_qgemm(11008, 4096, 1, 2, 1, 8, peaks)); print(res[-1], flush=True)
         res.append(bench_qgemm(32 * 11008, 4096, 1, 2, 1, 2, peaks)); print(res[-1], flush=True)
