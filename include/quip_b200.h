@@ -134,17 +134,6 @@ int quip_silu_mul(const void* gate, const void* up, void* out, int64_t n, void* 
  *                  forward with V.idx = NULL: idx[l] = u_idx_gate[v_idx_down[l]] | u_idx_up[v_idx_down[l]] << 16. */
 int quip_silu_mul_gather(const void* gate, const void* up, const uint32_t* idx, void* out, int64_t rows, int32_t n,
                          void* stream);
-/*   quip_rmsnorm_multi  quip_rmsnorm with permutations folded in: the residual may be read through an index
- *                  (s[j] = x[j] + residual[residual_idx[j]]: a projection output still in its N-side layout order) and the
- *                  normalised row is written to nout <= 3 outputs, outs[k][l] = y[out_idx[k][l]] (out_idx[k] NULL = identity):
- *                  the K-side layout orders of the projections that consume it (quip_qlinear_forward with V.idx = NULL).
- *   quip_rope_gather  quip_rope out of place with the N-side gathers of q_proj / k_proj folded in: x[j] = in[idx[j]]. */
-int quip_rmsnorm_multi(const void* x, const void* residual, const int32_t* residual_idx, const void* weight, void* sum_out,
-                       int32_t nout, void* const* outs, const int32_t* const* out_idx, int64_t rows, int32_t d, float eps,
-                       void* stream);
-int quip_rope_gather(const void* q_in, const int32_t* q_idx, const void* k_in, const int32_t* k_idx, void* q_out, void* k_out,
-                     const void* cos, const void* sin, int64_t rows, int32_t n_q_heads, int32_t n_kv_heads, int32_t head_dim,
-                     void* stream);
 
 /* Signature-compatible replacement of the reference's own native call (quant_cuda.vecquant3matmul quant.py:229-230,
  * vecquant4matmul zeroShot/models/quant.py:207-208): ONE token, fp32, on the REFERENCE's packed layout

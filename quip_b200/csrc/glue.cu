@@ -182,154 +182,6 @@ silu_mul_gather_kernel(const __half* __restrict__ g, const __half* __restrict__ 
   }
 }
 
-// RMSNorm with the permutations of the neighbouring incoherence sides folded in (fused Llama stack, many tokens):
-//   s = x + (r_idx ? r[r_idx[j]] : r[j])        the residual may still be in a projection's N-side layout order
-//   y = w * fp16(s * rsqrt(mean(s^2) + eps))    (same rounding points as rmsnorm_kernel)
-//   out_k[l] = y[idx_k[l]]  for up to three outputs: the K-side layout orders of the projections that consume y
-// One CTA per row; the residual row and the normalised row pass through shared memory for the 2-byte permuted reads.
-struct NormOuts {
-  __half* out[3];
-  const int32_t* idx[3];
-  int n;
-};
-
-__global__ void __launch_bounds__(1024)
-rmsnorm_multi_kernel(const __half* __restrict__ x, const __half* __restrict__ r, const int32_t* __restrict__ r_idx,
-                     const __half* __restrict__ w, __half* __restrict__ sum_out, NormOuts outs, int d, float eps) {
-  extern __shared__ __align__(16) unsigned char nm_raw[];
-  __half* rs = reinterpret_cast<__half*>(nm_raw);                 // [d] residual row (only with r_idx)
-  __half* ys = rs + d;                                            // [d] normalised row
-  __shared__ float red[32];
-  const int64_t row = blockIdx.x;
-  const int nvec = d >> 3;
-  if (r && r_idx) {
-    for (int c = threadIdx.x; c < nvec; c += blockDim.x)
-      reinterpret_cast<uint4*>(rs)[c] = ldg_nc_v4(reinterpret_cast<const uint4*>(r + row * d) + c);
-    __syncthreads();
-  }
-  H8 v[RN_MAXV];
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < RN_MAXV; ++i) {
-    const int c = threadIdx.x + i * blockDim.x;
-    if (c < nvec) {
-      v[i].v = reinterpret_cast<const uint4*>(x + row * d)[c];
-      if (r) {
-        H8 t;
-        if (r_idx) {
-          const int4 i0 = __ldg(reinterpret_cast<const int4*>(r_idx) + 2 * c), i1 = __ldg(reinterpret_cast<const int4*>(r_idx) + 2 * c + 1);
-          const int ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-#pragma unroll
-          for (int e = 0; e < 8; ++e) t.h[e] = rs[ii[e]];
-        } else {
-          t.v = reinterpret_cast<const uint4*>(r + row * d)[c];
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) v[i].h2[j] = __hadd2_rn(v[i].h2[j], t.h2[j]);
-        if (sum_out) reinterpret_cast<uint4*>(sum_out + row * d)[c] = v[i].v;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(v[i].h2[j]);
-        ss = fmaf(f.x, f.x, ss);
-        ss = fmaf(f.y, f.y, ss);
-      }
-    }
-  }
-  ss = warp_sum(ss);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  if (lane == 0) red[warp] = ss;
-  __syncthreads();
-  float tot = (lane < nwarps) ? red[lane] : 0.f;
-  tot = warp_sum(tot);
-  const float inv = rsqrtf(tot / (float)d + eps);
-  const uint4* wr = reinterpret_cast<const uint4*>(w);
-  bool any_perm = false;
-#pragma unroll
-  for (int k = 0; k < 3; ++k) any_perm |= (k < outs.n && outs.idx[k] != nullptr);
-#pragma unroll
-  for (int i = 0; i < RN_MAXV; ++i) {
-    const int c = threadIdx.x + i * blockDim.x;
-    if (c < nvec) {
-      H8 ww, o;
-      ww.v = wr[c];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = __half22float2(v[i].h2[j]);
-        const __half2 nn = __floats2half2_rn(f.x * inv, f.y * inv);
-        o.h2[j] = __hmul2_rn(ww.h2[j], nn);
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        if (k < outs.n && outs.idx[k] == nullptr) reinterpret_cast<uint4*>(outs.out[k] + row * d)[c] = o.v;
-      if (any_perm) reinterpret_cast<uint4*>(ys)[c] = o.v;
-    }
-  }
-  if (!any_perm) return;
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    if (k >= outs.n || outs.idx[k] == nullptr) continue;
-    const int4* ip = reinterpret_cast<const int4*>(outs.idx[k]);
-    for (int c = threadIdx.x; c < nvec; c += blockDim.x) {
-      const int4 i0 = __ldg(ip + 2 * c), i1 = __ldg(ip + 2 * c + 1);
-      const int ii[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
-      H8 o;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o.h[e] = ys[ii[e]];
-      reinterpret_cast<uint4*>(outs.out[k] + row * d)[c] = o.v;
-    }
-  }
-}
-
-// Rotary embedding with the output gathers of q_proj / k_proj folded in: the inputs are in the projections' N-side layout
-// order, the outputs in the standard [token][head][dim] order SDPA reads:
-//   x[j] = in[idx[j]];  out = fp16(fp16(x*cos) + fp16(rot(x)*sin))        (same roundings as rope_kernel)
-// One CTA per token row; the two input rows pass through shared memory.
-__global__ void __launch_bounds__(512)
-rope_gather_kernel(const __half* __restrict__ qin, const int32_t* __restrict__ qidx, const __half* __restrict__ kin,
-                   const int32_t* __restrict__ kidx, __half* __restrict__ qout, __half* __restrict__ kout,
-                   const __half* __restrict__ cs, const __half* __restrict__ sn, int nq, int nkv, int hd) {
-  extern __shared__ __align__(16) unsigned char rg_raw[];
-  __half* qs = reinterpret_cast<__half*>(rg_raw);                 // [nq * hd]
-  __half* ks = qs + (size_t)nq * hd;                              // [nkv * hd]
-  const int64_t row = blockIdx.x;
-  const int dq = nq * hd, dk = nkv * hd;
-  for (int c = threadIdx.x; c < (dq >> 3); c += blockDim.x)
-    reinterpret_cast<uint4*>(qs)[c] = ldg_nc_v4(reinterpret_cast<const uint4*>(qin + row * dq) + c);
-  for (int c = threadIdx.x; c < (dk >> 3); c += blockDim.x)
-    reinterpret_cast<uint4*>(ks)[c] = ldg_nc_v4(reinterpret_cast<const uint4*>(kin + row * dk) + c);
-  __syncthreads();
-  const int hv = hd >> 4, half_hd = hd >> 1;
-  const int items = (nq + nkv) * hv;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int c = it % hv, head = it / hv;
-    const bool isq = head < nq;
-    const __half* src = isq ? qs : ks;
-    const int32_t* idx = isq ? qidx : kidx;
-    const int base = (isq ? head : head - nq) * hd;
-    __half* dst = (isq ? qout + row * dq : kout + row * dk) + base;
-    H8 x1, x2, c1, c2, s1, s2, o1, o2;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int j1 = base + c * 8 + e, j2 = j1 + half_hd;
-      x1.h[e] = src[idx ? __ldg(idx + j1) : j1];
-      x2.h[e] = src[idx ? __ldg(idx + j2) : j2];
-    }
-    c1.v = *reinterpret_cast<const uint4*>(cs + row * hd + c * 8);
-    c2.v = *reinterpret_cast<const uint4*>(cs + row * hd + half_hd + c * 8);
-    s1.v = *reinterpret_cast<const uint4*>(sn + row * hd + c * 8);
-    s2.v = *reinterpret_cast<const uint4*>(sn + row * hd + half_hd + c * 8);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      o1.h2[j] = __hadd2_rn(__hmul2_rn(x1.h2[j], c1.h2[j]), __hmul2_rn(__hneg2(x2.h2[j]), s1.h2[j]));
-      o2.h2[j] = __hadd2_rn(__hmul2_rn(x2.h2[j], c2.h2[j]), __hmul2_rn(x1.h2[j], s2.h2[j]));
-    }
-    *reinterpret_cast<uint4*>(dst + c * 8) = o1.v;
-    *reinterpret_cast<uint4*>(dst + half_hd + c * 8) = o2.v;
-  }
-}
-
 int stream_grid(int64_t items, int threads) {
   static int sms = 0;
   if (!sms) {
@@ -416,64 +268,5 @@ extern "C" int quip_silu_mul_gather(const void* gate, const void* up, const uint
   silu_mul_gather_kernel<<<(unsigned)ceil_div(rows, rpc), SG_THREADS, smem, (cudaStream_t)stream>>>(
       (const __half*)gate, (const __half*)up, idx, (__half*)out, rows, n, rpc);
   QUIP_LAUNCHED("silu_mul_gather_kernel");
-  return QUIP_OK;
-}
-
-extern "C" int quip_rmsnorm_multi(const void* x, const void* residual, const int32_t* residual_idx, const void* weight,
-                                  void* sum_out, int32_t nout, void* const* outs, const int32_t* const* out_idx, int64_t rows,
-                                  int32_t d, float eps, void* stream) {
-  QUIP_CHECK_ARG(x && weight && outs && nout >= 1 && nout <= 3, "quip_rmsnorm_multi: null pointer or nout not in 1..3");
-  QUIP_CHECK_ARG(rows >= 0 && d > 0 && d % 8 == 0 && rows < (1ll << 31), "quip_rmsnorm_multi: bad sizes (d=%d)", d);
-  QUIP_CHECK_ARG(!sum_out || residual, "quip_rmsnorm_multi: sum_out without a residual");
-  QUIP_CHECK_ARG(!residual_idx || residual, "quip_rmsnorm_multi: residual_idx without a residual");
-  QUIP_CHECK_ARG(aligned16(x) && aligned16(weight) && aligned16(residual) && aligned16(sum_out) && aligned16(residual_idx),
-                 "quip_rmsnorm_multi: pointers must be 16-byte aligned");
-  if (rows == 0) return QUIP_OK;
-  NormOuts no{};
-  no.n = nout;
-  for (int k = 0; k < nout; ++k) {
-    QUIP_CHECK_ARG(outs[k] && aligned16(outs[k]) && aligned16(out_idx ? out_idx[k] : nullptr), "quip_rmsnorm_multi: output %d null or unaligned", k);
-    no.out[k] = (__half*)outs[k];
-    no.idx[k] = out_idx ? out_idx[k] : nullptr;
-  }
-  const int nvec = d / 8;
-  int threads = ((nvec + RN_MAXV - 1) / RN_MAXV + 31) / 32 * 32;
-  QUIP_CHECK_ARG(threads <= 1024, "quip_rmsnorm_multi: width %d exceeds %d", d, 1024 * RN_MAXV * 8);
-  const size_t smem = (size_t)2 * d * sizeof(__half);
-  static size_t done[64] = {0};
-  int dev = 0;
-  QUIP_CUDA(cudaGetDevice(&dev));
-  if (smem > 48 * 1024 && smem > done[dev & 63]) {
-    QUIP_CUDA(cudaFuncSetAttribute(rmsnorm_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done[dev & 63] = smem;
-  }
-  rmsnorm_multi_kernel<<<(unsigned)rows, threads, smem, (cudaStream_t)stream>>>(
-      (const __half*)x, (const __half*)residual, residual_idx, (const __half*)weight, (__half*)sum_out, no, d, eps);
-  QUIP_LAUNCHED("rmsnorm_multi_kernel");
-  return QUIP_OK;
-}
-
-extern "C" int quip_rope_gather(const void* q_in, const int32_t* q_idx, const void* k_in, const int32_t* k_idx, void* q_out,
-                                void* k_out, const void* cos, const void* sin, int64_t rows, int32_t n_q_heads,
-                                int32_t n_kv_heads, int32_t head_dim, void* stream) {
-  QUIP_CHECK_ARG(q_in && k_in && q_out && k_out && cos && sin, "quip_rope_gather: null pointer");
-  QUIP_CHECK_ARG(n_q_heads > 0 && n_kv_heads > 0 && head_dim > 0 && head_dim % 16 == 0, "quip_rope_gather: bad head geometry");
-  QUIP_CHECK_ARG(aligned16(q_in) && aligned16(k_in) && aligned16(q_out) && aligned16(k_out) && aligned16(cos) && aligned16(sin),
-                 "quip_rope_gather: pointers must be 16-byte aligned");
-  QUIP_CHECK_ARG(q_in != q_out && k_in != k_out, "quip_rope_gather: out of place only");
-  if (rows <= 0) return QUIP_OK;
-  const size_t smem = (size_t)(n_q_heads + n_kv_heads) * head_dim * sizeof(__half);
-  QUIP_CHECK_ARG(smem <= 200 * 1024, "quip_rope_gather: rows of %zu bytes do not fit shared memory", smem);
-  static size_t done[64] = {0};
-  int dev = 0;
-  QUIP_CUDA(cudaGetDevice(&dev));
-  if (smem > 48 * 1024 && smem > done[dev & 63]) {
-    QUIP_CUDA(cudaFuncSetAttribute(rope_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done[dev & 63] = smem;
-  }
-  rope_gather_kernel<<<(unsigned)rows, 512, smem, (cudaStream_t)stream>>>(
-      (const __half*)q_in, q_idx, (const __half*)k_in, k_idx, (__half*)q_out, (__half*)k_out, (const __half*)cos,
-      (const __half*)sin, n_q_heads, n_kv_heads, head_dim);
-  QUIP_LAUNCHED("rope_gather_kernel");
   return QUIP_OK;
 }

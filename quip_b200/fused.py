@@ -77,35 +77,6 @@ class CudaGlue:
         return out
 
 
-    def rmsnorm_multi(self, x, weight, eps, out_idx, residual=None, residual_idx=None):
-        """quip_rmsnorm_multi: s = x + residual[residual_idx]; y = norm(s) written once per entry of `out_idx` (None =
-        standard order, an int32 tensor = that permutation).  Returns (s or None, [outputs])."""
-        self._check(x, weight, residual)
-        d = x.shape[-1]
-        rows = x.numel() // d
-        outs = [torch.empty_like(x) for _ in out_idx]
-        s = torch.empty_like(x) if residual is not None else None
-        optr = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
-        iptr = (C.c_void_p * len(outs))(*[None if i is None else i.data_ptr() for i in out_idx])
-        with torch.cuda.device(x.device):
-            _lib.check(_lib.load().quip_rmsnorm_multi(
-                x.data_ptr(), residual.data_ptr() if residual is not None else None,
-                residual_idx.data_ptr() if residual_idx is not None else None, weight.data_ptr(),
-                s.data_ptr() if s is not None else None, len(outs), optr, iptr, rows, d, C.c_float(eps), self._stream(x)))
-        return s, outs
-
-    def rope_gather(self, q, q_idx, k, k_idx, cos, sin, head_dim):
-        """quip_rope_gather: rotary on q[..., q_idx], k[..., k_idx] (idx None = identity), out of place."""
-        self._check(q, k, cos, sin)
-        rows = q.numel() // q.shape[-1]
-        qo, ko = torch.empty_like(q), torch.empty_like(k)
-        with torch.cuda.device(q.device):
-            _lib.check(_lib.load().quip_rope_gather(q.data_ptr(), None if q_idx is None else q_idx.data_ptr(), k.data_ptr(),
-                                                    None if k_idx is None else k_idx.data_ptr(), qo.data_ptr(), ko.data_ptr(),
-                                                    cos.data_ptr(), sin.data_ptr(), rows, q.shape[-1] // head_dim,
-                                                    k.shape[-1] // head_dim, head_dim, self._stream(q)))
-        return qo, ko
-
     def silu_mul_gather(self, gate, up, idx):
         """silu(gate[..., ig]) * up[..., iu] with idx = ig | iu << 16 per output feature (int32 tensor): quip_silu_mul_gather."""
         self._check(gate, up)
@@ -143,34 +114,6 @@ def mlp_layout_plan(mlp):
     return plan
 
 
-def layer_layout_plan(layer):
-    """Index vectors for folding the gathers of the 4096-wide sides of a packed Llama decoder layer into its glue kernels
-    (many tokens): the K-side gathers of q / k / v and gate / up into the norm that produces their input (one permuted copy per
-    consumer), the N-side gathers of q / k into the rotary kernel, those of o_proj / down_proj into the residual add of the
-    next norm.  (v keeps its output gather: SDPA reads it in head order; o_proj keeps its input gather: SDPA writes it.)
-    A side kernel without its gather runs its vectorised stage-in / stage-out instead of a 2-byte permute through shared
-    memory.  None when a layer is not packed or a gather cannot be skipped.  Cached on the layer."""
-    from .quant import QuantLinear
-    a, mlp = layer.self_attn, layer.mlp
-    mods = dict(q=a.q_proj, k=a.k_proj, v=a.v_proj, o=a.o_proj, gate=mlp.gate_proj, up=mlp.up_proj, down=mlp.down_proj)
-    if not all(isinstance(m, QuantLinear) for m in mods.values()):
-        return None
-    dev = mods['q'].qweight.device
-    cached = getattr(layer, '_quip_layout_plan', None)
-    if cached is not None and cached[0] == dev:
-        return cached[1]
-    plan = None
-    ok = (dev.type == 'cuda' and mlp_layout_plan(mlp) is not None
-          and all(mods[n].layout_variant_ok(skip_in=True) for n in ('q', 'k', 'v', 'gate', 'up'))
-          and all(mods[n].layout_variant_ok(skip_out=True) for n in ('q', 'k', 'o', 'down')))
-    if ok:
-        i32 = lambda t: None if t is None else t.to(torch.int32).contiguous()      # noqa: E731
-        plan = dict(v_in={n: i32(mods[n].gather_index('v')) for n in ('q', 'k', 'v', 'gate', 'up')},
-                    u_out={n: i32(mods[n].gather_index('u')) for n in ('q', 'k', 'o', 'down')})
-    layer._quip_layout_plan = (dev, plan)
-    return plan
-
-
 def enabled():
     """The fused stack is opt-in (QUIP_FUSED_LAYER=1) until it has been measured on a B200."""
     return os.environ.get('QUIP_FUSED_LAYER') == '1'
@@ -192,69 +135,12 @@ def supports(model, h, kwargs):
     return hd % 16 == 0 and cfg.hidden_size % 8 == 0 and cfg.intermediate_size % 8 == 0
 
 
-def _run_siblings(mods, inputs, variants):
-    """mods[i].forward on inputs[i] with layout variant variants[i]; on the members' side streams when they form a group."""
-    grp = getattr(mods[0], '_group', None)
-    if grp is not None and list(grp.members) == list(mods) and inputs[0].is_cuda:
-        return grp.run_each(inputs, variants)
-    return [m._forward_impl(x, variant=v) for m, x, v in zip(mods, inputs, variants)]
-
-
-def _llama_stack_folded(layers, plans, h, kwargs, ops):
-    """llama_stack with the gathers of the 4096-wide sides folded into the glue kernels (layer_layout_plan): the hidden states
-    are bit-identical to the unfolded stack -- only where the permutations happen changes."""
-    cos, sin = kwargs['position_embeddings']
-    cos, sin = cos[0].contiguous(), sin[0].contiguous()
-    mask = kwargs.get('attention_mask')
-    S = h.shape[1]
-    h = h.contiguous()
-    pend = pend_idx = None                 # previous layer's MLP output in down_proj's N-side layout order, and that order
-    for layer, P in zip(layers, plans):
-        a, mlp = layer.self_attn, layer.mlp
-        n1, n2 = layer.input_layernorm, layer.post_attention_layernorm
-        hd = a.head_dim
-        vi, uo = P['v_in'], P['u_out']
-        s, (xq, xk, xv) = ops.rmsnorm_multi(h, n1.weight, n1.variance_epsilon, [vi['q'], vi['k'], vi['v']], residual=pend,
-                                            residual_idx=pend_idx)
-        if s is not None:
-            h = s
-        q, k, v = _run_siblings([a.q_proj, a.k_proj, a.v_proj], [xq, xk, xv], [(True, True), (True, True), (True, False)])
-        q, k = ops.rope_gather(q, uo['q'], k, uo['k'], cos, sin, hd)
-        nq, nkv = q.shape[-1] // hd, k.shape[-1] // hd
-        qh = q.view(1, S, nq, hd).transpose(1, 2)
-        kh = k.view(1, S, nkv, hd).transpose(1, 2)
-        vh = v.view(1, S, nkv, hd).transpose(1, 2)
-        extra = {}
-        if mask is None:
-            extra['enable_gqa'] = True
-        elif nkv != nq:
-            kh = kh.repeat_interleave(nq // nkv, dim=1)
-            vh = vh.repeat_interleave(nq // nkv, dim=1)
-        o = F.scaled_dot_product_attention(qh, kh, vh, attn_mask=mask, dropout_p=0.0, scale=a.scaling,
-                                           is_causal=(mask is None and S > 1), **extra)
-        o = o.transpose(1, 2).reshape(1, S, nq * hd).contiguous()
-        ao = a.o_proj.forward_layout(o, skip_out=True)
-        h, (xg, xu) = ops.rmsnorm_multi(h, n2.weight, n2.variance_epsilon, [vi['gate'], vi['up']], residual=ao,
-                                        residual_idx=uo['o'])
-        g, u = _run_siblings([mlp.gate_proj, mlp.up_proj], [xg, xu], [(True, True), (True, True)])
-        act = ops.silu_mul_gather(g, u, mlp_layout_plan(mlp))
-        pend = mlp.down_proj.forward_layout(act, skip_in=True, skip_out=True)
-        pend_idx = uo['down']
-    if pend is None:
-        return h
-    return h + (pend if pend_idx is None else pend.index_select(-1, pend_idx.long()))
-
-
 def llama_stack(layers, h, kwargs, ops=None, trace=None, fold_gathers=None):
     """`for layer in layers: h = layer(h, **kwargs)` for LlamaDecoderLayers on one sample h (1, S, hidden).  `trace`: an optional
     list that receives (layer index, stage name, tensor) for tools/glue_bisect.py."""
     ops = ops or CudaGlue()
     if fold_gathers is None:
-        fold_gathers = trace is None and os.environ.get('QUIP_FOLD_GATHERS', '1') != '0'
-    if fold_gathers and h.shape[1] > 32 and hasattr(ops, 'rmsnorm_multi') and os.environ.get('QUIP_FOLD_GATHERS', '1') != 'mlp':
-        plans = [layer_layout_plan(layer) for layer in layers]          # many tokens: the one-kernel sides take the gathers
-        if layers and all(p is not None for p in plans):
-            return _llama_stack_folded(layers, plans, h, kwargs, ops)
+        fold_gathers = trace is None and os.environ.get('QUIP_FOLD_GATHERS', '1') == '1'
     cos, sin = kwargs['position_embeddings']
     cos, sin = cos[0].contiguous(), sin[0].contiguous()                     # (S, head_dim)
     mask = kwargs.get('attention_mask')

@@ -337,36 +337,6 @@ class SiblingGroup:
         return y
 
 
-    def run_each(self, inputs, variants):
-        """Every member on ITS OWN input (the same activations in the members' different K-side layout orders) and with its
-        own layout variant: members[i]._forward_impl(inputs[i], variant=variants[i]), member 0 on the caller's stream, the
-        others on the side streams.  Returns the outputs, all ready for the caller's stream."""
-        dev = inputs[0].device
-        if self.streams is None or self.streams[0].device != dev:
-            self.streams = [torch.cuda.Stream(device=dev) for _ in self.members[1:]]
-        cur = torch.cuda.current_stream(dev)
-        capturing = torch.cuda.is_current_stream_capturing()
-        ready = torch.cuda.Event()
-        ready.record(cur)
-        outs, events = [None] * len(self.members), []
-        for j in range(1, len(self.members)):
-            st = self.streams[j - 1]
-            st.wait_event(ready)
-            with torch.cuda.stream(st):
-                outs[j] = self.members[j]._forward_impl(inputs[j], variant=variants[j])
-                ev = torch.cuda.Event()
-                ev.record(st)
-            if not capturing:
-                inputs[j].record_stream(st)
-            events.append(ev)
-        outs[0] = self.members[0]._forward_impl(inputs[0], variant=variants[0])
-        for j, ev in enumerate(events, 1):
-            cur.wait_event(ev)
-            if not capturing:
-                outs[j].record_stream(cur)
-        return outs
-
-
 def group_siblings(model):
     """Group q/k/v and gate/up (Llama) or q/k/v (OPT) QuantLinears of every decoder layer.  Returns the groups."""
     groups = []
