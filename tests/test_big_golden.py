@@ -28,3 +28,26 @@ def test_big_layer_packs_with_bit_exact_codes():
     uo, vo = plan_side(tp.U, 'U').order, plan_side(tp.V, 'V').order
     assert torch.equal(ql.codes(), tp.codes[uo][:, vo])
     assert int(ql.meta[1]) == 1                               # qfn 'b': symmetric grid
+
+
+def test_fp32_restatement_agrees_with_the_reference_outputs_on_the_cpu():
+    """quip_b200/selfcheck.restated_forward (the checker bench.py and the GPU tests use) against the live reference's y_ref of
+    the golden layers and of the 4096 x 4096 layer: it is an independent, correct statement of the layer."""
+    import numpy as np
+    from conftest import LAYER_NAMES, load_layer, parts_to_torch
+    from quip_b200 import quant as Q
+    from quip_b200.selfcheck import rel_err, restated_forward
+    for name in LAYER_NAMES:
+        parts, z = load_layer(name)
+        tp = parts_to_torch(parts)
+        N, K = tp.codes.shape
+        ql = Q.QuantLinear(infeatures=K, outfeatures=N, **Q.spec_from_parts(tp))
+        ql.pack_parts(tp)
+        y = restated_forward(ql, torch.from_numpy(z['x']))
+        assert rel_err(y, torch.from_numpy(z['y_ref'].astype(np.float32))) < 6e-4, name      # the reference's own fp16 roundings
+    tp, z = load_big_layer()
+    N, K = tp.codes.shape
+    ql = Q.QuantLinear(infeatures=K, outfeatures=N, **Q.spec_from_parts(tp))
+    ql.pack_parts(tp)
+    y = restated_forward(ql, torch.from_numpy(z['x']))
+    assert rel_err(y, torch.from_numpy(z['y_ref']).float()) < 6e-4
