@@ -268,6 +268,35 @@ def _device_ms(fn, reps, warm):
     return e0.elapsed_time(e1) / reps
 
 
+def _replay_ms(fn, reps=3):
+    """Device milliseconds of fn() replayed from a CUDA graph: what the timed step does, and independent of the host (eager
+    launches of several ranks on a host with few cores are host-bound, which says nothing about the kernels).  Falls back to
+    eager timing when the capture fails."""
+    try:
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side, capture_error_mode='thread_local'):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        graph.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    except Exception:
+        torch.cuda.synchronize()
+        return _device_ms(fn, reps=reps, warm=2)
+
+
 def _ulp_flip_hooks(mods, rate, seed=0):
     """Forward hooks that move a random fraction `rate` of each module's fp16 outputs by one ulp: the control of pick_glue."""
     gens = {}
@@ -367,10 +396,11 @@ def pick_glue(model, prime):
                     for hk in hooks:
                         hk.remove()
             control = sorted(ctrl)[1]
-            times = {name: _device_ms(fn, reps=3, warm=2) / len(layers) for name, fn in (('hf', hf), ('fused', fu))}
+            timer = _replay_ms if h.is_cuda else (lambda fn: _device_ms(fn, reps=3, warm=2))
+            times = {name: timer(fn) / len(layers) for name, fn in (('hf', hf), ('fused', fu))}
             info.update(rel_err_vs_hf_layers=err, control_rel_err_hf_vs_hf_with_ulp_flips=control, control_runs=ctrl,
                         control_flip_rate=rate, ms_per_layer_hf=times['hf'], ms_per_layer_fused=times['fused'],
-                        note='eager launches, first two decoder layers, one 2048-token sample; control = the HF layers with '
+                        note='CUDA-graph replays (device time), first two decoder layers, one 2048-token sample; control = the HF layers with '
                              'one-ulp flips in their norm outputs at the measured rate (median of 3 seeds)')
             stack_ok = err < 1e-3 or err <= 3.0 * control
             if exact and norm_ok and stack_ok and times['fused'] < times['hf']:
