@@ -2,8 +2,8 @@
 
 SURVEY section 8(f) rank 1: the quantisation-time hot loop the reference runs as d sequential column updates in
 Python (vector_balance.py:155-199 `round_ldl`, :218-291 the blocked variant, :139-152 / :202-215 the sorted
-"RG" wrappers, :500-530 the dispatch in quantize_weight_vecbal).  This file restates the algorithm so that a GPU implementation (next on the
-list in DESIGN.md) has a bit-exact checker for its integer codes:
+"RG" wrappers, :500-530 the dispatch in quantize_weight_vecbal).  This file restates the algorithm; it is the checker for the integer codes of the GPU
+implementation (quip_b200/csrc/ldlq.cu through quip_b200/quantize.py, tests/test_gpu_quantize.py):
 
   * L = strictly lower part of the unit-diagonal Cholesky factor of H (vector_balance.py:174-176);
   * columns are rounded last to first, column i seeing the feedback (w - w_hat)[:, i:] @ L[i:, i]
