@@ -553,7 +553,7 @@ def pp_main(a, base, rank, world):
     cfg = model_config(a.model) if not a.layers else model_config(a.model, num_hidden_layers=a.layers)
     L = cfg.num_hidden_layers
     lo, hi = pipeline.stage_ranges(L, world)[rank]
-    model = build_synthetic_model(cfg, dev, bits=2, incoh='blocked', rescale=True, seed=0, seqlen=SEQ, layer_range=(lo, hi),
+    model = build_synthetic_model(cfg, dev, bits=2, incoh=a.incoh, rescale=True, seed=0, seqlen=SEQ, layer_range=(lo, hi),
                                   head=(rank == world - 1))
     model.seqlen = SEQ
     from quip_b200.quant import group_siblings
@@ -656,15 +656,20 @@ def main():
     ap.add_argument('--model', default='llama7b', choices=['llama7b', 'llama70b', 'opt1.3b', 'opt30b', 'opt125m'],
                     help='llama7b = BASELINE configs[2], the headline; the others are the remaining configs')
     ap.add_argument('--parallelism', default='dp', choices=['dp', 'pp'])
+    ap.add_argument('--incoh', default='blocked', choices=['blocked', 'kron'],
+                    help="butterfly structure of U / V: 'blocked' = one orthogonal block per position, what --incoh_processing runs "
+                         "(opt.py:596, method.py:34-35; the headline); 'kron' = one block per stage (pre_proj_extra 1, method.py:38-39): "
+                         "the factor bytes drop from n(p1+p2) to p1^2+p2^2 per side (not the headline configuration)")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-decode', action='store_true', help='skip the one-token decode legs (quick runs)')
     a = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
+    structure = 'blocked butterflies' if a.incoh == 'blocked' else 'Kronecker butterflies (pre_proj_extra 1): NOT the headline structure'
     pretty = {'llama7b': 'Llama-2-7B', 'llama70b': 'Llama-2-70B', 'opt1.3b': 'OPT-1.3b', 'opt30b': 'OPT-30b', 'opt125m': 'OPT-125m'}[a.model]
     base = dict(metric=f'tokens/sec 2-bit {pretty} (per-layer eval path, seq 2048)', unit='tokens/s', n_gpus=a.gpus,
                 steps=a.steps, warmup=a.warmup, higher_is_better=True, scaling='weak', vs_baseline=None, data='synthetic',
-                config=dict(workload=f'{pretty} 2-bit --incoh_processing (blocked butterflies + rescale), seq 2048, batch 1 '
+                config=dict(workload=f'{pretty} 2-bit --incoh_processing ({structure} + rescale), seq 2048, batch 1 '
                                      'per step, random codes / random orthogonal factors / random-init embeddings',
                             parallelism=f'dp{a.gpus}', l2='inputs larger than L2: each step streams 3.5 GB of packed '
                                                           'weights + butterfly factors',
@@ -705,7 +710,7 @@ def main():
     lib = _lib.load()
 
     cfg = model_config(a.model) if not a.layers else model_config(a.model, num_hidden_layers=a.layers)
-    model = build_synthetic_model(cfg, dev, bits=2, incoh='blocked', rescale=True, seed=rank, seqlen=SEQ)
+    model = build_synthetic_model(cfg, dev, bits=2, incoh=a.incoh, rescale=True, seed=rank, seqlen=SEQ)
     model.seqlen = SEQ
     groups = []
     if os.environ.get('QUIP_NO_OVERLAP') != '1':
@@ -912,6 +917,24 @@ def main():
                                                  note='quip_b200.decode.GraphDecoder: the same decode step (attention, norms, '
                                                       'static KV cache of 64, lm_head) replayed from one CUDA graph, batch 1')
         except Exception as e:                      # the decode leg is an extra; never lose the headline over it
+            out['decode'] = dict(error=repr(e)[:200])
+    if world == 1 and not a.no_decode and family == 'opt':
+        # the model the reference's benchmark() is written for (opt.py:431-482): eager HF decode and the graph decode
+        try:
+            for g in groups:
+                g.dissolve()
+            from quip_b200.decode import graph_decode_benchmark, graph_decode_throughput
+            sec, _ = evalloop.decode_benchmark(model, ids_dev[0][:, :48])
+            gsec, _ = graph_decode_benchmark(model, ids_dev[0][:, :48], max_len=64)
+            sweep = {}
+            for bsz in (1, 8, 32):
+                tps, step_ms = graph_decode_throughput(model, bsz, steps=24, max_len=32)
+                sweep[str(bsz)] = dict(tokens_per_s=tps, ms_per_step=step_ms)
+            out['decode'] = dict(hf_decode=dict(tokens_per_s=1.0 / sec, median_ms_per_token=sec * 1e3, tokens=48),
+                                 graph_decode=dict(tokens_per_s=1.0 / gsec, median_ms_per_token=gsec * 1e3, tokens=48,
+                                                   note='quip_b200.decode.GraphDecoder (OPT step, torch glue), static KV cache of 64'),
+                                 graph_decode_batch_sweep=sweep)
+        except Exception as e:
             out['decode'] = dict(error=repr(e)[:200])
     if world == 1 and not a.no_cpu_baseline:
         v, per_layer, cores, sample = cpu_reference_arm(1, 1, a.model)[:4]

@@ -1,4 +1,4 @@
-"""Token-by-token decode of a packed Llama model from one CUDA graph.
+"""Token-by-token decode of a packed Llama or OPT model from one CUDA graph.
 
 The reference's `benchmark()` (opt.py:431-482, llama.py via the same code) times an eager HF forward per
 token with a growing KV cache; with the few-token kernels of this package one token's GPU work is a few
@@ -11,7 +11,8 @@ is the same computation with everything a CUDA graph needs made static:
 
 The decoder layers' own modules are reused (input_layernorm, the seven QuantLinear / nn.Linear projections,
 post_attention_layernorm, final norm, lm_head): same weights, same kernels as `model(...)`; only the glue
-between them is restated.  Llama family only (MHA or GQA); OPT keeps the eager path.
+between them is restated.  Llama (MHA or GQA; torch glue or the kernels of csrc/glue.cu) and OPT (the model benchmark() is
+written for, opt.py:431-482: learned positions, LayerNorm with bias, ReLU MLP; torch glue).
 """
 import math
 
@@ -29,19 +30,27 @@ class GraphDecoder:
         """ops: provider of the fused glue kernels (quip_b200.fused.CudaGlue; picked up automatically when
         QUIP_FUSED_LAYER=1 on a CUDA device), None for the torch glue."""
         cfg = model.config
-        assert cfg.model_type == 'llama', 'GraphDecoder covers the Llama family'
+        assert cfg.model_type in ('llama', 'opt'), 'GraphDecoder covers the Llama and OPT families'
+        self.family = cfg.model_type
         self.model, self.max_len, self.batch = model, int(max_len), int(batch)
         self.dev = next(iter(model.parameters())).device
-        self.layers = list(model.model.layers)
         self.nh = cfg.num_attention_heads
-        self.nkv = getattr(cfg, 'num_key_value_heads', None) or self.nh
-        self.hd = getattr(cfg, 'head_dim', None) or cfg.hidden_size // self.nh
         dt = torch.float16
-        # rotary table with the model's own module (HF default rope: positions 0 .. max_len-1)
-        pos = torch.arange(self.max_len, device=self.dev)[None, :]
-        with torch.no_grad():
-            cos, sin = model.model.rotary_emb(torch.zeros(1, 1, cfg.hidden_size, device=self.dev, dtype=dt), pos)
-        self.cos, self.sin = cos[0].to(dt).contiguous(), sin[0].to(dt).contiguous()        # (max_len, head_dim)
+        if self.family == 'llama':
+            self.layers = list(model.model.layers)
+            self.nkv = getattr(cfg, 'num_key_value_heads', None) or self.nh
+            self.hd = getattr(cfg, 'head_dim', None) or cfg.hidden_size // self.nh
+            # rotary table with the model's own module (HF default rope: positions 0 .. max_len-1)
+            pos = torch.arange(self.max_len, device=self.dev)[None, :]
+            with torch.no_grad():
+                cos, sin = model.model.rotary_emb(torch.zeros(1, 1, cfg.hidden_size, device=self.dev, dtype=dt), pos)
+            self.cos, self.sin = cos[0].to(dt).contiguous(), sin[0].to(dt).contiguous()        # (max_len, head_dim)
+        else:
+            dec = model.model.decoder
+            assert self.max_len <= cfg.max_position_embeddings, 'OPT has learned positions: max_len beyond the table'
+            self.layers = list(dec.layers)
+            self.nkv = self.nh
+            self.hd = cfg.hidden_size // self.nh
         L, B = len(self.layers), self.batch
         self.k_cache = torch.zeros(L, B, self.nkv, self.max_len, self.hd, dtype=dt, device=self.dev)
         self.v_cache = torch.zeros_like(self.k_cache)
@@ -53,7 +62,9 @@ class GraphDecoder:
         self._pos_host = 0
         # q/k/v and gate/up read the same input: their chains of few-token kernels run on parallel branches
         self._side = [torch.cuda.Stream(device=self.dev) for _ in range(2)] if self.dev.type == 'cuda' else None
-        if ops is None and self.dev.type == 'cuda':
+        if self.family != 'llama':
+            ops = None                                     # the fused glue kernels are the Llama layer's
+        elif ops is None and self.dev.type == 'cuda':
             from . import fused
             if fused.enabled() and getattr(cfg, 'hidden_act', 'silu') == 'silu' and self.hd % 16 == 0:
                 ops = fused.CudaGlue()
@@ -120,6 +131,8 @@ class GraphDecoder:
 
     # one decode step on the static buffers (what the graph records)
     def _step(self):
+        if self.family == 'opt':
+            return self._step_opt()
         if self.ops is not None:
             return self._step_fused()
         m = self.model.model
@@ -152,6 +165,39 @@ class GraphDecoder:
             gate, up = self._parallel(x, [mlp.gate_proj, mlp.up_proj])
             h = h + mlp.down_proj(F.silu(gate) * up)
         h = m.norm(h)
+        self.logits = self.model.lm_head(h)[:, 0, :]
+        self.position.add_(1)
+
+    # OPT (modeling_opt.OPTDecoderLayer): learned positions (index position + 2), pre- or post-LayerNorm, q scaled before
+    # the dot product, ReLU between fc1 and fc2; biases live inside the (Quant)Linear modules
+    def _step_opt(self):
+        d = self.model.model.decoder
+        B, nh, hd = self.batch, self.nh, self.hd
+        pos = self.position
+        h = d.embed_tokens(self.tokens)[:, None, :]                                        # (B, 1, word_embed_proj_dim)
+        if d.project_in is not None:
+            h = d.project_in(h)
+        h = h + F.embedding(pos + d.embed_positions.offset, d.embed_positions.weight)[None]
+        mask = (self._arange <= pos)[None, None, None, :]
+        for li, layer in enumerate(self.layers):
+            a, before = layer.self_attn, layer.do_layer_norm_before
+            x = layer.self_attn_layer_norm(h) if before else h
+            q, k, v = self._parallel(x, [a.q_proj, a.k_proj, a.v_proj])
+            q = (q * a.scaling).view(B, 1, nh, hd).transpose(1, 2)                         # scaled first, as the HF module does
+            self.k_cache[li].index_copy_(2, pos, k.view(B, 1, nh, hd).transpose(1, 2))
+            self.v_cache[li].index_copy_(2, pos, v.view(B, 1, nh, hd).transpose(1, 2))
+            o = F.scaled_dot_product_attention(q, self.k_cache[li], self.v_cache[li], attn_mask=mask, scale=1.0)
+            h = h + a.out_proj(o.transpose(1, 2).reshape(B, 1, nh * hd))
+            if not before:
+                h = layer.self_attn_layer_norm(h)
+            x = layer.final_layer_norm(h) if before else h
+            h = h + layer.fc2(layer.activation_fn(layer.fc1(x)))
+            if not before:
+                h = layer.final_layer_norm(h)
+        if d.final_layer_norm is not None:
+            h = d.final_layer_norm(h)
+        if d.project_out is not None:
+            h = d.project_out(h)
         self.logits = self.model.lm_head(h)[:, 0, :]
         self.position.add_(1)
 

@@ -164,5 +164,10 @@ def opt_multigpu(model, gpus):
     model.gpus = gpus
 
 
-def benchmark(model, input_ids, check=False):
+def benchmark(model, input_ids, check=False, graph=False):
+    """The reference's benchmark() (opt.py:431-482): token-by-token decode with a KV cache.  graph=True replays the same
+    step from one CUDA graph (quip_b200.decode.GraphDecoder) instead of the eager HF forward."""
+    if graph:
+        from .decode import graph_decode_benchmark
+        return graph_decode_benchmark(model, input_ids, check=check)
     return evalloop.decode_benchmark(model, input_ids, check=check)

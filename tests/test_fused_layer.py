@@ -197,3 +197,28 @@ def test_bench_decode_glue_check_logic(monkeypatch):
     ok, worst, control = bench.decode_glue_ok(m, torch.device('cpu'))
     assert not ok and worst > 2e-3 and worst > 3 * control
     monkeypatch.delenv('QUIP_FUSED_LAYER', raising=False)
+
+
+@pytest.mark.parametrize('before', [True, False])
+def test_opt_decoder_steps_equal_hf_decode_with_kv_cache_on_cpu(before):
+    """GraphDecoder's OPT step (learned positions with the offset of 2, pre- / post-LayerNorm, scaled q, ReLU MLP, biases)
+    against the HF OPT forward with a KV cache -- the loop the reference's benchmark() runs (opt.py:431-482) -- in fp32 on
+    the CPU.  word_embed_proj_dim != hidden_size exercises project_in / project_out (OPT-350m's shape)."""
+    from transformers import OPTConfig, OPTForCausalLM
+    from quip_b200.decode import GraphDecoder
+    torch.manual_seed(0)
+    cfg = OPTConfig(hidden_size=64, ffn_dim=128, num_hidden_layers=2, num_attention_heads=4, vocab_size=199,
+                    max_position_embeddings=32, word_embed_proj_dim=64 if before else 48, do_layer_norm_before=before)
+    m = OPTForCausalLM(cfg).float().eval()
+    ids = torch.randint(0, 199, (2, 9), generator=torch.Generator().manual_seed(6))
+    with torch.no_grad():
+        dec = GraphDecoder(m, max_len=16, batch=2)
+        dec.k_cache, dec.v_cache = dec.k_cache.float(), dec.v_cache.float()
+        past = None
+        for i in range(ids.shape[1]):
+            out = m(ids[:, i:i + 1], past_key_values=past, use_cache=True)
+            past = out.past_key_values
+            got = dec.step(ids[:, i])
+            assert torch.allclose(got, out.logits[:, -1], rtol=2e-4, atol=2e-4), i
+    with pytest.raises(AssertionError):
+        GraphDecoder(m, max_len=64)                        # beyond the learned position table

@@ -102,3 +102,48 @@ def test_graphed_sample_nll_equals_eager_and_feeds_eval_ppl():
     assert abs(ppl_graph - ppl_eager) <= 1e-3 * ppl_eager
     with pytest.raises(ValueError):
         stepper(ids[0][:, :32])
+
+
+def test_opt_graph_decoder_matches_eager_hf_decode():
+    """The OPT step of GraphDecoder (packed q/k/v/out_proj/fc1/fc2 with bias, LayerNorm, learned positions) against the HF
+    forward with a KV cache -- the reference's benchmark() loop (opt.py:431-482); graph replay == the eager step."""
+    from transformers import OPTConfig
+    import bench
+    from quip_b200.decode import GraphDecoder
+    from quip_b200.opt import benchmark
+    from quip_b200.synth import build_synthetic_model
+    cfg = OPTConfig(hidden_size=256, ffn_dim=1024, num_hidden_layers=2, num_attention_heads=4, vocab_size=320,
+                    max_position_embeddings=128, word_embed_proj_dim=256)
+    model = build_synthetic_model(cfg, torch.device('cuda:0'), bits=2, incoh='blocked', rescale=True, seed=6, seqlen=64)
+    ids = torch.randint(0, 320, (1, 14), generator=torch.Generator().manual_seed(3)).cuda()
+    dec_mod = model.model.decoder
+    norms = [m for layer in dec_mod.layers for m in (layer.self_attn_layer_norm, layer.final_layer_norm)] + [dec_mod.final_layer_norm]
+
+    def hf_decode(flip):
+        past, res = None, []
+        for i in range(ids.shape[1]):
+            hooks = bench._ulp_flip_hooks(norms, 3e-5, seed=i) if flip else []
+            try:
+                out = model(ids[:, i:i + 1], past_key_values=past, use_cache=True)
+            finally:
+                for hk in hooks:
+                    hk.remove()
+            past = out.past_key_values
+            res.append(out.logits[0, -1].float())
+        return res
+    with torch.no_grad():
+        want, ctrl = hf_decode(False), hf_decode(True)
+        dec = GraphDecoder(model, max_len=32)
+        eager = [dec.step(ids[0, i:i + 1])[0].float().clone() for i in range(ids.shape[1])]
+        dec.reset()
+        dec.capture()
+        graph = [dec.step(ids[0, i:i + 1])[0].float().clone() for i in range(ids.shape[1])]
+    worst = control = 0.0
+    for i, (w, e, g, c) in enumerate(zip(want, eager, graph, ctrl)):
+        assert torch.equal(e, g), i
+        worst = max(worst, float((g - w).norm() / w.norm()))
+        control = max(control, float((c - w).norm() / w.norm()))
+    assert worst < max(2e-3, 3.0 * control), (worst, control)
+    sec, ppl = benchmark(model, ids.cpu(), check=True, graph=True)
+    sec0, ppl0 = benchmark(model, ids.cpu(), check=True)
+    assert sec > 0 and abs(ppl - ppl0) / ppl0 < 2e-2

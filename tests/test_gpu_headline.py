@@ -94,6 +94,29 @@ def test_quantlinear_at_bench_shapes(K, N):
         assert torch.equal(y, ql(x[:M]))
 
 
+@pytest.mark.parametrize('K,N', [(4096, 11008), (11008, 4096)])
+def test_kronecker_layers_at_bench_shapes(K, N):
+    """`bench.py --incoh kron`: one block per stage (method.py:38-39), every CTA of a pass reading the SAME factor -- the 688-wide
+    dense pass with a shared block, the one-kernel 4096 sides with shared factors and the few-token routes."""
+    from quip_b200 import quant as Q
+    from quip_b200.selfcheck import reference_dense_weight, rel_err, restated_forward
+    from quip_b200.synth import synth_layer_parts
+    tp = synth_layer_parts(K=K, N=N, bits=2, incoh='kron', rescale=True, bias=False, seed=K + N + 1)
+    ql = Q.QuantLinear(infeatures=K, outfeatures=N, **Q.spec_from_parts(tp))
+    ql.pack_parts(tp)
+    ql = ql.cuda()
+    W_ref = reference_dense_weight(tp, 'cuda')
+    x = _inputs(2048, K, K + N + 1)
+    for M in (2048, 2043, 40, 16, 1):
+        y = ql(x[:M])
+        e_model = rel_err(y, restated_forward(ql, x[:M]))
+        e_ref = rel_err(y, torch.nn.functional.linear(x[:M], W_ref))
+        _report('quantlinear_bench_shape_kron', K=K, N=N, M=M, rel_err_vs_restatement=e_model, rel_err_vs_reference_dense=e_ref)
+        assert e_model < 1e-3, (K, N, M, e_model)
+        assert e_ref < 1e-3, (K, N, M, e_ref)
+        assert torch.equal(y, ql(x[:M]))
+
+
 def test_golden_4096_layer_from_the_live_reference():
     """tests/golden/layer_big_4096.npz: a q_proj-sized Linear quantized by the reference's own Balance flow (ldlq, 2 bits,
     --incoh_processing).  Its 16-token y_ref through every token-count route, including 2048 tokens (the 16 rows

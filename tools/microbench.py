@@ -247,6 +247,13 @@ def main():
                 res.append(bench_pass(n, p, nblk, st, M)); print(res[-1], flush=True)
             res.append(bench_gather(4096, M)); print(res[-1], flush=True)
             res.append(bench_gather(11008, M)); print(res[-1], flush=True)
+    if 'structure' in what:
+        # blocked (one factor block per position: n(p1+p2) factor elements per side) against Kronecker (one block per stage,
+        # p1^2+p2^2: every CTA of a pass reads the same block) butterflies on the three Llama-2-7B QuantLinear shapes
+        for (N, K) in shapes:
+            for M in (1, 2048):
+                for incoh in ('blocked', 'kron'):
+                    r = bench_layer(N, K, M, 2, incoh, peaks, copies=4 if M == 1 else 2); res.append(r); print(r, flush=True)
     if 'decode' in what:
         # one token through the three Llama-2-7B QuantLinear shapes, blocked butterflies + rescale (the as-run default)
         lib = _lib.load()
