@@ -414,7 +414,7 @@ def pick_glue(model, prime):
 
 
 def decode_glue_ok(model, dev):
-    """The decode step with the fused glue (GraphDecoder._step_fused) against the torch-glue step on the same model: eight
+    """The decode step with the fused glue (GraphDecoder._layers_fused) against the torch-glue step on the same model: eight
     tokens, two sequences.  As in pick_glue the two differ only by one-ulp flips of the norm outputs, which 32 random-init
     layers amplify; the logits difference is therefore judged against a control -- the torch-glue step against itself with
     such flips injected at the measured rate (<= 3x the control, or < 2e-3 outright)."""
@@ -557,7 +557,7 @@ def pp_main(a, base, rank, world):
                                   head=(rank == world - 1))
     model.seqlen = SEQ
     from quip_b200.quant import group_siblings
-    group_siblings(model)
+    groups = group_siblings(model)
     if family == 'llama' and os.environ.get('QUIP_FUSED_LAYER') is None:
         os.environ['QUIP_FUSED_LAYER'] = '1'
     total = a.warmup + a.steps
@@ -593,13 +593,29 @@ def pp_main(a, base, rank, world):
         dist.all_gather(allst, torch.tensor([stage_ms], device=dev))
         worst = torch.tensor([check['worst'] if check and check['worst'] is not None else 0.0], device=dev)
         dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        n_launch = int(stage_launches(stage, lib) * a.steps)
+        decode = None
+        if not a.no_decode:
+            # the reference's benchmark() on the placed model (opt.py:384-482): token-by-token decode across the stages
+            try:
+                for g in groups:
+                    g.dissolve()
+                r = pipeline.pp_decode_benchmark(model, arch, ids_host[0][:, :48], dev, max_len=64)
+                decode = dict(tokens_per_s=1.0 / r['latency_s'], median_ms_per_token=r['latency_s'] * 1e3,
+                              teacher_forced_tokens_per_s=1.0 / r['pipelined_s'], tokens=r['tokens'], stages=r['stages'],
+                              note='quip_b200.pipeline.PipelinedDecoder: one GraphDecoder stage (CUDA graph, own KV cache of 64) '
+                                   'per rank, (1, 1, hidden) fp16 hidden state over the per-link communicators; tokens_per_s = '
+                                   'all ranks synchronised around every token (host clock), teacher_forced = free-running feed '
+                                   'of given ids (stages overlap across tokens), batch 1')
+            except Exception as e:
+                decode = dict(error=repr(e)[:200])
     if rank == 0:
         ms = float(ms[0])
         stages = [float(x[0]) for x in allst]
         value = a.steps * SEQ / (ms / 1e3)
         ideal = SEQ / (max(stages) / 1e3)
         out = dict(base, value=value, ms_per_step=ms / a.steps, dtype='f16', impl='ours', scaling='strong',
-                   gpu_launches=int(stage_launches(stage, lib) * a.steps),
+                   gpu_launches=n_launch,
                    e2e=dict(value=value, unit='tokens/s', h2d_bytes_per_step=SEQ * 8, d2h_bytes_per_step=4,
                             api='quip_b200.pipeline.PipelineStage.run (host token ids, pinned)'),
                    pipeline=dict(stages=world, layers_per_stage=[list(r) for r in pipeline.stage_ranges(L, world)],
@@ -610,6 +626,8 @@ def pp_main(a, base, rank, world):
                                            'sample ahead, sends double-buffered' % (SEQ, cfg.hidden_size)),
                    selfcheck=dict(worst_rel_err_over_stages=float(worst[0]), tolerance=1e-3), clocks=clk.summary())
         out['config'] = dict(base['config'], parallelism=f'pp{world}')
+        if decode is not None:
+            out['decode'] = decode
         print(json.dumps(out))
     dist.destroy_process_group()
 

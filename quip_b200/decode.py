@@ -26,16 +26,22 @@ def _rotate_half(x):
 
 
 class GraphDecoder:
-    def __init__(self, model, max_len=256, batch=1, ops=None):
+    def __init__(self, model, max_len=256, batch=1, ops=None, layer_range=None, first=True, last=True):
         """ops: provider of the fused glue kernels (quip_b200.fused.CudaGlue; picked up automatically when
-        QUIP_FUSED_LAYER=1 on a CUDA device), None for the torch glue."""
+        QUIP_FUSED_LAYER=1 on a CUDA device), None for the torch glue.
+
+        layer_range=(lo, hi), first, last: one STAGE of a layer pipeline (the reference's opt_multigpu / llama_multigpu
+        placement, opt.py:384-428) -- decoder layers lo..hi-1 with their own KV cache; a stage that is not the first reads
+        the hidden state of the token from `h_in`, one that is not the last leaves it in `h_out` (static buffers, so the
+        stage is still one graph); quip_b200.pipeline.PipelinedDecoder moves them between ranks."""
         cfg = model.config
         assert cfg.model_type in ('llama', 'opt'), 'GraphDecoder covers the Llama and OPT families'
         self.family = cfg.model_type
         self.model, self.max_len, self.batch = model, int(max_len), int(batch)
         self.dev = next(iter(model.parameters())).device
         self.nh = cfg.num_attention_heads
-        dt = torch.float16
+        dt = model.get_input_embeddings().weight.dtype     # fp16 on the GPU path; fp32 in the CPU tests
+        self.first, self.last = bool(first), bool(last)
         if self.family == 'llama':
             self.layers = list(model.model.layers)
             self.nkv = getattr(cfg, 'num_key_value_heads', None) or self.nh
@@ -51,7 +57,12 @@ class GraphDecoder:
             self.layers = list(dec.layers)
             self.nkv = self.nh
             self.hd = cfg.hidden_size // self.nh
+        lo, hi = layer_range or (0, len(self.layers))
+        assert 0 <= lo < hi <= len(self.layers), (lo, hi)
+        self.layers = self.layers[lo:hi]
         L, B = len(self.layers), self.batch
+        self.h_in = None if self.first else torch.zeros(B, 1, cfg.hidden_size, dtype=dt, device=self.dev)
+        self.h_out = None if self.last else torch.zeros(B, 1, cfg.hidden_size, dtype=dt, device=self.dev)
         self.k_cache = torch.zeros(L, B, self.nkv, self.max_len, self.hd, dtype=dt, device=self.dev)
         self.v_cache = torch.zeros_like(self.k_cache)
         self.position = torch.zeros(1, dtype=torch.long, device=self.dev)
@@ -92,13 +103,16 @@ class GraphDecoder:
         self.k_cache.zero_()
         self.v_cache.zero_()
 
-    # the same step with the glue of csrc/glue.cu: 4 launches per layer instead of ~30 (at one token every torch
-    # elementwise op is a launch-latency-bound graph node)
-    def _step_fused(self):
-        m, ops = self.model.model, self.ops
+    # ---- the layers of the stage, three kinds of glue.  Each takes the hidden state entering the stage and returns
+    # (h, pend): the residual stream and a branch output still to be added to it (None when already added).
+
+    # csrc/glue.cu: 4 launches per layer instead of ~30 (at one token every torch elementwise op is a launch-latency-bound
+    # graph node); the residual add of a branch rides on the next RMSNorm
+    def _layers_fused(self, h):
+        ops = self.ops
         B, nh, nkv, hd = self.batch, self.nh, self.nkv, self.hd
         pos = self.position
-        h = m.embed_tokens(self.tokens)[:, None, :].contiguous()                           # (B, 1, hidden)
+        h = h.contiguous()
         cos = self.cos.index_select(0, pos).expand(B, hd).contiguous()                     # one row per sequence
         sin = self.sin.index_select(0, pos).expand(B, hd).contiguous()
         mask = (self._arange <= pos)[None, None, None, :]
@@ -124,21 +138,11 @@ class GraphDecoder:
             h, x = ops.rmsnorm(h, n2.weight, n2.variance_epsilon, residual=a.o_proj(o))
             gate, up = self._parallel(x, [mlp.gate_proj, mlp.up_proj])
             pend = mlp.down_proj(ops.silu_mul(gate, up))
-        fn = m.norm
-        _, h = ops.rmsnorm(h, fn.weight, fn.variance_epsilon, residual=pend)
-        self.logits = self.model.lm_head(h)[:, 0, :]
-        self.position.add_(1)
+        return h, pend
 
-    # one decode step on the static buffers (what the graph records)
-    def _step(self):
-        if self.family == 'opt':
-            return self._step_opt()
-        if self.ops is not None:
-            return self._step_fused()
-        m = self.model.model
+    def _layers_llama(self, h):
         B, nh, nkv, hd = self.batch, self.nh, self.nkv, self.hd
         pos = self.position
-        h = m.embed_tokens(self.tokens)[:, None, :]                                        # (B, 1, hidden)
         cos = self.cos.index_select(0, pos)[None, None]                                    # (1, 1, 1, hd)
         sin = self.sin.index_select(0, pos)[None, None]
         mask = (self._arange <= pos)[None, None, None, :]                                  # (1, 1, 1, max_len)
@@ -164,20 +168,13 @@ class GraphDecoder:
             mlp = layer.mlp
             gate, up = self._parallel(x, [mlp.gate_proj, mlp.up_proj])
             h = h + mlp.down_proj(F.silu(gate) * up)
-        h = m.norm(h)
-        self.logits = self.model.lm_head(h)[:, 0, :]
-        self.position.add_(1)
+        return h, None
 
-    # OPT (modeling_opt.OPTDecoderLayer): learned positions (index position + 2), pre- or post-LayerNorm, q scaled before
-    # the dot product, ReLU between fc1 and fc2; biases live inside the (Quant)Linear modules
-    def _step_opt(self):
-        d = self.model.model.decoder
+    # OPT (modeling_opt.OPTDecoderLayer): pre- or post-LayerNorm, q scaled before the dot product, ReLU between fc1 and fc2;
+    # biases live inside the (Quant)Linear modules
+    def _layers_opt(self, h):
         B, nh, hd = self.batch, self.nh, self.hd
         pos = self.position
-        h = d.embed_tokens(self.tokens)[:, None, :]                                        # (B, 1, word_embed_proj_dim)
-        if d.project_in is not None:
-            h = d.project_in(h)
-        h = h + F.embedding(pos + d.embed_positions.offset, d.embed_positions.weight)[None]
         mask = (self._arange <= pos)[None, None, None, :]
         for li, layer in enumerate(self.layers):
             a, before = layer.self_attn, layer.do_layer_norm_before
@@ -194,11 +191,47 @@ class GraphDecoder:
             h = h + layer.fc2(layer.activation_fn(layer.fc1(x)))
             if not before:
                 h = layer.final_layer_norm(h)
-        if d.final_layer_norm is not None:
-            h = d.final_layer_norm(h)
-        if d.project_out is not None:
-            h = d.project_out(h)
-        self.logits = self.model.lm_head(h)[:, 0, :]
+        return h, None
+
+    def _embed(self):
+        """Token (and, for OPT, learned position: index position + 2) embeddings of the step: (B, 1, hidden)."""
+        if self.family == 'llama':
+            return self.model.model.embed_tokens(self.tokens)[:, None, :]
+        d = self.model.model.decoder
+        h = d.embed_tokens(self.tokens)[:, None, :]
+        if d.project_in is not None:
+            h = d.project_in(h)
+        return h + F.embedding(self.position + d.embed_positions.offset, d.embed_positions.weight)[None]
+
+    def _head(self, h, pend):
+        """Final norm (fused with the pending residual add on the glue-kernel path) -> lm_head: logits (B, vocab)."""
+        if self.family == 'llama':
+            fn = self.model.model.norm
+            if self.ops is not None:
+                _, h = self.ops.rmsnorm(h, fn.weight, fn.variance_epsilon, residual=pend)
+            else:
+                h = fn(h)
+        else:
+            d = self.model.model.decoder
+            if d.final_layer_norm is not None:
+                h = d.final_layer_norm(h)
+            if d.project_out is not None:
+                h = d.project_out(h)
+        return self.model.lm_head(h)[:, 0, :]
+
+    # one decode step of the stage on the static buffers (what the graph records)
+    def _step(self):
+        h = self._embed() if self.first else self.h_in
+        if self.family == 'opt':
+            h, pend = self._layers_opt(h)
+        elif self.ops is not None:
+            h, pend = self._layers_fused(h)
+        else:
+            h, pend = self._layers_llama(h)
+        if self.last:
+            self.logits = self._head(h, pend)
+        else:
+            self.h_out.copy_(h if pend is None else h + pend)   # fp16 add: the rounding the fused residual add performs
         self.position.add_(1)
 
     def capture(self):

@@ -208,3 +208,77 @@ def pp_eval(model, arch, testenc, dev, layers_dist=None, verbose=False, graph=No
         print(ppl)
     model.config.use_cache = use_cache
     return ppl
+
+
+class PipelinedDecoder:
+    """Token-by-token decode with a KV cache across a layer pipeline: the reference's `benchmark()` on a model placed by
+    `opt_multigpu` / `llama_multigpu` (opt.py:384-482, llama.py:361-471), one process per GPU.
+
+    Every rank owns one `decode.GraphDecoder` stage (its contiguous layer range, the KV cache of those layers, one CUDA graph
+    on CUDA devices); the (batch, 1, hidden) fp16 hidden state of the token travels over the per-link communicators of
+    `pair_groups()`.  The token ids are given on every rank (the benchmark is teacher-forced, opt.py:461-470), so nothing
+    flows back from the last stage and stage r can start token i+1 while stage r+1 works on token i."""
+
+    def __init__(self, model, arch, dev, max_len=256, batch=1, layers_dist=None, graph=None, ops=None):
+        from .decode import GraphDecoder
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.first, self.last = self.rank == 0, self.rank == self.world - 1
+        self.dev = torch.device(dev)
+        lo, hi = stage_ranges(len(arch.layers(model)), self.world, layers_dist)[self.rank]
+        self.groups = pair_groups() if self.world > 1 else []
+        self.dec = GraphDecoder(model, max_len=max_len, batch=batch, ops=ops, layer_range=(lo, hi), first=self.first, last=self.last)
+        if self.dev.type == 'cuda' if graph is None else graph:
+            self.dec.capture()
+
+    def reset(self):
+        self.dec.reset()
+
+    @torch.no_grad()
+    def step(self, tokens):
+        """tokens (batch,) on every rank -> logits (batch, vocab) on the last rank, None elsewhere."""
+        if not self.first:
+            dist.recv(self.dec.h_in, src=self.rank - 1, group=self.groups[self.rank - 1])
+        out = self.dec.step(tokens.to(self.dev))
+        if not self.last:
+            dist.send(self.dec.h_out, dst=self.rank + 1, group=self.groups[self.rank])
+        return out if self.last else None
+
+
+@torch.no_grad()
+def pp_decode_benchmark(model, arch, input_ids, dev, max_len=None, check=False, layers_dist=None, graph=None):
+    """`benchmark()` (opt.py:431-482) over the pipeline: feeds input_ids (1, T) token by token.  Returns a dict, the same on
+    every rank: `latency_s` = median seconds per token with all ranks synchronised around every token (what a generation loop
+    would see), `pipelined_s` = seconds per token of the free-running teacher-forced feed (stages overlapped across tokens), and
+    `ppl` of the fed sequence with check (computed on the last rank, as opt.py:469-475 does on the last GPU)."""
+    import time
+
+    import torch.nn.functional as F
+    dev = torch.device(dev)
+    ids = input_ids.reshape(-1).to(dev)
+    T = int(ids.numel())
+    pd = PipelinedDecoder(model, arch, dev, max_len=max_len or T, batch=1, layers_dist=layers_dist, graph=graph)
+    sync = torch.cuda.synchronize if dev.type == 'cuda' else (lambda: None)
+    times, tot = [], torch.zeros((), dtype=torch.float32, device=dev)
+    for i in range(T):
+        sync()
+        dist.barrier()
+        t0 = time.perf_counter()
+        logits = pd.step(ids[i:i + 1])
+        sync()
+        dist.barrier()
+        times.append(time.perf_counter() - t0)
+        if check and pd.last and i != T - 1:
+            tot += F.cross_entropy(logits.float(), ids[i + 1:i + 2])
+    pd.reset()
+    sync()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(T):
+        pd.step(ids[i:i + 1])
+    sync()
+    dist.barrier()
+    free = (time.perf_counter() - t0) / T
+    stats = torch.tensor([sorted(times)[len(times) // 2], free, float(tot) if pd.last else 0.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)     # times: slowest rank; the NLL sum lives on the last rank only
+    ppl = float(torch.exp(stats[2] / (T - 1))) if check and T > 1 else None
+    return dict(latency_s=float(stats[0]), pipelined_s=float(stats[1]), ppl=ppl, tokens=T, stages=pd.world)

@@ -57,3 +57,55 @@ def test_stage_ranges_follow_the_reference_rule():
     assert stage_ranges(80, 3, '20:30:30') == [(0, 20), (20, 50), (50, 80)]    # --layers-dist, llama.py:400-413
     with pytest.raises(AssertionError):
         stage_ranges(80, 2, '20:30')
+
+
+def _decode_worker(rank, world, port, family, out):
+    sys.path.insert(0, ROOT)
+    os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.set_num_threads(2)
+    from quip_b200 import evalloop, pipeline
+    pipeline.init_distributed(backend='gloo')
+    torch.manual_seed(0)
+    if family == 'opt':
+        from transformers import OPTConfig, OPTForCausalLM
+        model = OPTForCausalLM(OPTConfig(hidden_size=64, ffn_dim=128, num_hidden_layers=5, num_attention_heads=4, vocab_size=199,
+                                         max_position_embeddings=32, word_embed_proj_dim=64)).float().eval()
+        arch = evalloop.OPT
+    else:
+        from transformers import LlamaConfig, LlamaForCausalLM
+        model = LlamaForCausalLM(LlamaConfig(hidden_size=64, intermediate_size=128, num_hidden_layers=5, num_attention_heads=4,
+                                             num_key_value_heads=2, vocab_size=199, max_position_embeddings=32)).float().eval()
+        arch = evalloop.LLAMA
+    ids = torch.randint(0, 199, (1, 10), generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        ref_sec, ref_ppl = evalloop.decode_benchmark(model, ids, check=True)      # the whole model in one process (benchmark())
+        res = pipeline.pp_decode_benchmark(model, arch, ids, 'cpu', max_len=16, check=True)
+        # logits of the last stage, token by token, against the HF forward with a KV cache
+        pd = pipeline.PipelinedDecoder(model, arch, 'cpu', max_len=16, batch=1)
+        past, worst = None, 0.0
+        for i in range(ids.shape[1]):
+            got = pd.step(ids[0, i:i + 1])
+            o = model(ids[:, i:i + 1], past_key_values=past, use_cache=True)
+            past = o.past_key_values
+            if pd.last:
+                worst = max(worst, float((got - o.logits[:, -1]).abs().max()))
+            else:
+                assert got is None
+    out[rank] = (res, ref_ppl, worst)
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+@pytest.mark.parametrize('family,world', [('opt', 2), ('llama', 3)])
+def test_pipelined_decode_matches_the_single_process_benchmark(family, world):
+    """benchmark() over a layer pipeline (opt_multigpu + benchmark, opt.py:384-482): every rank one GraphDecoder stage with its own
+    KV cache, hidden states over the per-link groups; 5 layers on 2 / 3 ranks (uneven stages, a middle stage)."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_decode_worker, args=(world, _free_port(), family, out), nprocs=world, join=True)
+    assert len(out) == world
+    for rank in range(world):
+        res, ref_ppl, worst = out[rank]
+        assert res['stages'] == world and res['tokens'] == 10 and res['latency_s'] > 0 and res['pipelined_s'] > 0
+        assert abs(res['ppl'] - ref_ppl) / ref_ppl < 1e-4, (rank, res['ppl'], ref_ppl)
+        assert worst < 2e-4, (rank, worst)
