@@ -893,10 +893,11 @@ def main():
                roofline=dict(bound='tensor', kernel='qgemm_tc_kernel<2,256> (tcgen05 packed GEMM)', achieved=achieved,
                              peak=pk['tflops_sustained'], unit='TFLOP/s', frac=(achieved / pk['tflops_sustained']) if achieved else None,
                              traffic=traffic, traffic_note=traffic_note, launches_timed=int(tn.value), kernel_ms_per_step=tms.value / a.steps,
-                             share_of_step=tms.value / serial_ms,
+                             share_of_step=tms.value / ms, share_of_serial_replay=tms.value / serial_ms,
                              measured_in=('serial replay of the same K steps with CUDA events around every launch '
-                                          '(sibling-stream overlap off, %.2f ms/step); the headline timed region runs '
-                                          'with the overlap on' % (serial_ms / a.steps)), peak_source=pk['source'] + ', sustained bf16 (kernel timed inside a long step)'),
+                                          '(sibling-stream overlap off, eager launches: %.2f ms/step, host gaps included); '
+                                          'share_of_step = its summed launch time / the timed step (one graph replay, overlap '
+                                          'on); the ncu launch list of the same command: profiles/launches_r02.json' % (serial_ms / a.steps)), peak_source=pk['source'] + ', sustained bf16 (kernel timed inside a long step)'),
                selfcheck=check, clocks=clk.summary())
     if world == 1 and not a.no_decode and a.model == 'llama7b':
         try:
