@@ -50,6 +50,7 @@ int side_fewtok(const QuipSide* sd, const __half* in, __half* out, int64_t M, in
 static int g_side_fused = 1;     // many tokens: a whole side (gather + both passes [+ row sums]) in one kernel when the blocks allow
 static int g_pdl = 1;            // few-token kernels: programmatic dependent launch (weights prefetched under the previous kernel)
 static int g_use_gemv = 1;       // few-token contractions: whole-K qgemv kernel (0: the split-K kernel)
+static int g_sk_ksplit = 0;      // split-K kernel: cap on the number of K splits (0: the heuristic of skinny_pick_ksplit)
 static int g_side_fewtok = 0;    // <= 8 tokens: both passes of a side in ONE launch (rot_side_fewtok.cu), 3 launches per linear.
                                  // Correct on every shape but measured SLOWER than two pass launches (every CTA stages the whole
                                  // token vector): an ablation, off by default (profiles/README.md)
@@ -168,6 +169,7 @@ static int run_qgemm_untimed(const QuipLinearDesc* d, const __half* x2, const fl
         continue;
       }
       int ksplit = skinny_pick_ksplit(d->N, d->K, 64, mc);
+      if (g_sk_ksplit > 0 && g_sk_ksplit < ksplit) ksplit = g_sk_ksplit;   // experiments: fewer splits only (the plan sized the partials)
       if (int e = qgemm_skinny(d, x2 + m0 * d->K, bias, z + m0 * d->N, mc, ksplit,
                                reinterpret_cast<float*>(ws + p.part), reinterpret_cast<int*>(ws), s))
         return e;
@@ -206,6 +208,7 @@ extern "C" int quip_config(const char* key, int value) {
   if (!strcmp(key, "gv_int")) { g_gv_int = value; return QUIP_OK; }
   if (!strcmp(key, "gv_persist")) { g_gv_persist = value; return QUIP_OK; }
   if (!strcmp(key, "gather_rows")) { g_gather_rows = value; return QUIP_OK; }
+  if (!strcmp(key, "sk_ksplit")) { g_sk_ksplit = value; return QUIP_OK; }
   if (!strcmp(key, "pass_min_tiles")) { g_pass_min_tiles = value > 0 ? value : 1; return QUIP_OK; }
   set_error("quip_config: unknown key '%s'", key);
   return QUIP_ERR_ARG;

@@ -250,18 +250,21 @@ static int launch_skinny(const QuipLinearDesc* d, const __half* x, const __half*
   return QUIP_OK;
 }
 
-// Heuristic split: enough CTAs for >= 2 per SM, K slices of at least 512 -- and small enough that the staged
-// activations of M tokens fit shared memory (K = 28672 with 32 tokens needs 16 slices).
+// Heuristic split.  Every K split costs a round trip of fp32 partials (write, fence, counter, the last CTA reads them all), and
+// that -- not the staging of the activations -- is what the kernel waits for at 9..32 tokens: on 4096 x 4096 with 32 tokens
+// 8 splits take 36.6 us, 2 splits 17.0 us; with 16 tokens 15.7 against 10.3-10.8 us (profiles/mb_skinny_r02.json).  So: just
+// enough splits for about one CTA per SM, K slices of at least 512, and as many more as the staged activations of M tokens
+// need to fit shared memory (K = 28672 with 32 tokens: 16 slices).
 int skinny_pick_ksplit(int N, int K, int rows_per_cta, int M) {
   int tiles = ceil_div(N, rows_per_cta);
   int ksb = K / 128;
   int ks = 1;
-  while (tiles * ks < 296 && ksb / (ks * 2) >= 4) ks *= 2;
+  while (tiles * ks < 128 && ksb / (ks * 2) >= 4) ks *= 2;
   const int tok = M <= 8 ? 8 : (M <= 16 ? 16 : 32);
   auto smem = [&](int k) {
     return (size_t)tok * (ceil_div(ksb, k) * 128 + SK_XPAD) * sizeof(__half) + (size_t)(SK_WARPS * tok * 72 + tok) * sizeof(float);
   };
-  while (smem(ks) > 200 * 1024 && ks < ksb) ks *= 2;
+  while (smem(ks) > 216 * 1024 && ks < ksb) ks *= 2;
   return ks;
 }
 

@@ -206,7 +206,8 @@ def test_one_launch_sides_for_a_handful_of_tokens(K, N, bits, incoh, bias):
             y1 = ql(x[:M]).float()
             launches = lib.quip_launch_count() - before
             assert float((y1 - want[:M]).norm() / want[:M].norm()) < 1e-3, (M, 'vs fp32 restatement')
-            assert float((y1 - y0).norm() / y0.norm()) < 1e-3, (M, 'vs the two-pass route')     # that one rounds the intermediate to fp16
+            # the two-pass route rounds the intermediate to fp16: two results, each within 1e-3 of the restatement
+            assert float((y1 - y0).norm() / y0.norm()) < 2e-3, (M, 'vs the two-pass route')
             assert torch.equal(y1, ql(x[:M]).float())
             assert launches <= 7, (M, launches)
             if max(K, N) <= 4096 or (M == 1 and max(K, N) <= 11008):   # both sides fit shared memory (tokens + factor rows)

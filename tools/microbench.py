@@ -247,6 +247,24 @@ def main():
                 res.append(bench_pass(n, p, nblk, st, M)); print(res[-1], flush=True)
             res.append(bench_gather(4096, M)); print(res[-1], flush=True)
             res.append(bench_gather(11008, M)); print(res[-1], flush=True)
+    if 'skinny' in what:
+        # 9..32 tokens (batched decode): the split-K contraction alone (by number of K splits) and whole QuantLinears
+        lib = _lib.load()
+        for (N, K) in shapes:
+            copies = max(2, int(300e6 // (N * K // 4)))
+            for M in (12, 16, 24, 32):
+                for ks in (0, 1, 2, 4):
+                    lib.quip_config(b'sk_ksplit', ks)
+                    try:
+                        r = bench_qgemm(N, K, M, 2, 1, copies, peaks); r['sk_ksplit'] = ks; res.append(r)
+                    except Exception as e:                      # a K slice that does not fit shared memory
+                        print(dict(N=N, K=K, M=M, sk_ksplit=ks, error=str(e)[-60:]), flush=True)
+                        continue
+                    print({k: (round(v, 2) if isinstance(v, float) else v) for k, v in r.items() if k in ('N', 'K', 'M', 'us', 'hbm_frac', 'sk_ksplit')}, flush=True)
+        lib.quip_config(b'sk_ksplit', 0)
+        for (N, K) in shapes:
+            for M in (8, 16, 32):
+                r = bench_layer(N, K, M, 2, 'blocked', peaks, copies=4); res.append(r); print(r, flush=True)
     if 'structure' in what:
         # blocked (one factor block per position: n(p1+p2) factor elements per side) against Kronecker (one block per stage,
         # p1^2+p2^2: every CTA of a pass reads the same block) butterflies on the three Llama-2-7B QuantLinear shapes
