@@ -107,42 +107,23 @@ pass_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, cons
   asm volatile("griddepcontrol.wait;" ::: "memory");
 
   // ---- stage the tokens of this CTA's blocks ----
-  // Every load of a thread is requested before the first value is used: a token loop that waits for its loads four at a
-  // time costs one global round trip per four tokens (7 us per pass at 32 tokens against 2 us at one).
   if (vec_in) {
     const int nq = (b_last - b_first + 1) * p / 4;         // 8-byte groups per token (p % 16 == 0)
-    constexpr int VB = 4;                                  // copies in flight per thread
-    for (int e0 = tid; e0 < nq * M; e0 += VB * FT_WARPS * 32) {
-      uint2 v[VB];
-#pragma unroll
-      for (int j = 0; j < VB; ++j) {
-        const int e = e0 + j * FT_WARPS * 32;
-        v[j] = make_uint2(0u, 0u);
-        if (e < nq * M) {
-          const int m = e / nq, qd = e - m * nq;
-          v[j] = *reinterpret_cast<const uint2*>(in + (int64_t)m * n + (int64_t)b_first * p + 4 * qd);
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < VB; ++j) {
-        const int e = e0 + j * FT_WARPS * 32;
-        if (e < nq * M) {
-          const int m = e / nq, qd = e - m * nq;
-          *reinterpret_cast<uint2*>(xs + m * xld + 4 * qd) = v[j];
-        }
-      }
+    for (int e = tid; e < nq * M; e += FT_WARPS * 32) {
+      const int m = e / nq, qd = e - m * nq;
+      *reinterpret_cast<uint2*>(xs + m * xld + 4 * qd) =
+          *reinterpret_cast<const uint2*>(in + (int64_t)m * n + (int64_t)b_first * p + 4 * qd);
     }
   } else {
 #pragma unroll
     for (int i = 0; i < FT_XPT; ++i) {
       const int e = tid + i * FT_WARPS * 32;
       if (src[i] >= 0) {
-        __half v[8 * NG];
-#pragma unroll
-        for (int m = 0; m < 8 * NG; ++m) v[m] = m < M ? __ldg(in + (int64_t)m * n + src[i]) : __float2half_rn(0.f);
-#pragma unroll
-        for (int m = 0; m < 8 * NG; ++m)
-          if (m < M) xs[m * xld + e] = in_scale ? __float2half_rn(__half2float(v[m]) * ssc[i]) : v[m];
+#pragma unroll 4
+        for (int m = 0; m < M; ++m) {
+          const float v = __half2float(__ldg(in + (int64_t)m * n + src[i]));
+          xs[m * xld + e] = in_scale ? __float2half_rn(v * ssc[i]) : __float2half_rn(v);
+        }
       }
     }
   }
@@ -239,7 +220,6 @@ gather_fewtok_kernel(const __half* __restrict__ in, __half* __restrict__ out, in
   }
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
-#pragma unroll 4
   for (int m = 0; m < M; ++m) {
     __align__(16) __half v[8];
     const __half* row = in + (int64_t)m * n;
