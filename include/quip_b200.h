@@ -195,6 +195,8 @@ int quip_timing_read(int path, double* total_ms, int64_t* launches, double* flop
  *   "gv_int" (1)      qgemv: int8 tensor-core path for 2-/4-bit and <= 5 tokens (0: fp16 path)
  *   "gv_tma" (1), "gv_cw" (16), "gv_rbc" (0 = auto), "gv_persist" (1)   variants of the cooperative int8 kernel
  *   "gv_stream" (32)  streaming int8 kernel when N/16 >= value * SMs (0: never)
+ *   "sk_ksplit" (0)   split-K kernel (9..32 tokens): cap on the number of K splits, only ever lowering the heuristic's choice
+ *                     (the workspace is sized for that); 0 = the heuristic
  *   "gather_rows", "pass_min_tiles"   tune the many-token un-projection kernels */
 int quip_config(const char* key, int value);
 
